@@ -1,0 +1,139 @@
+/* mpm_b200 — C ABI of the B200-native MLS-MPM substep.
+ *
+ * Drop-in boundary for the hot path of kekeblom/mpm: everything Simulation::advance()
+ * (reference src/mpm.cu:323-329) does on the device, plus the buffer management around it
+ * (src/mpm.cu:197-215, 278-314).  Plain pointers and sizes only; no C++ or torch types cross
+ * this boundary.  All int-returning functions return 0 on success and a non-zero CUDA/NCCL
+ * derived code otherwise (text via mpm_last_error); no exceptions cross the ABI.  One handle =
+ * one device = one host thread at a time; distinct handles are independent.
+ *
+ * Data crossing the boundary keeps the reference layouts:
+ *   particle  = MLS_APIC_Particle, 104 bytes AoS: u8 material_type (+3 pad), x[3], v[3],
+ *               F[9] column-major, C[9] column-major, Jp
+ *               (reference include/types.h:24-35, include/TransferScheme.h:46-54)
+ *   material  = MMSnow<Particle>, 7 floats (reference include/MaterialModel.cuh:23-24,47-48,70-72)
+ *   grid node = float4 (px|vx, py|vy, pz|vz, m), index N*N*i + N*j + k (reference src/mpm.cu:49,55,66)
+ */
+#ifndef MPM_B200_H
+#define MPM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPM_B200_ABI_VERSION 1
+
+/* which MaterialModel alias the kernels are instantiated for (reference include/mpm.cuh:25) */
+enum { MPM_MODEL_SNOW = 0, MPM_MODEL_FIXED_COROTATED = 1 };
+/* svd3 arithmetic: EXACT reproduces the reference svd3 bit for bit; FAST contracts to FMA and
+ * uses the hardware rsqrt approximation (deviation reported by the tests) */
+enum { MPM_SVD_EXACT = 0, MPM_SVD_FAST = 1 };
+/* stage indices for mpm_get_stage_times */
+enum { MPM_STAGE_SORT = 0, MPM_STAGE_RESET = 1, MPM_STAGE_P2G = 2, MPM_STAGE_GRID = 3, MPM_STAGE_G2P = 4,
+       MPM_STAGE_EXCHANGE = 5, MPM_STAGE_COUNT = 6 };
+
+/* replaces the reference's 104-byte particle record at the boundary */
+typedef struct MpmParticle {
+  uint8_t material_type;
+  uint8_t pad_[3];
+  float x[3];
+  float v[3];
+  float F[9]; /* column-major */
+  float C[9]; /* column-major */
+  float Jp;
+} MpmParticle;
+
+/* replaces MMSnow<Particle> (trivially copyable, memcpy'd to the device, src/mpm.cu:198-201) */
+typedef struct MpmMaterial {
+  float particleVolume;
+  float particleMass;
+  float mu0;
+  float lambda0;
+  float hardening;
+  float plast_clamp_lower;
+  float plast_clamp_higher;
+} MpmMaterial;
+
+/* replaces SimulationParameters (include/TransferScheme.h:6-29) + the compile-time aliases */
+typedef struct MpmParams {
+  float dt;             /* --dt */
+  uint32_t N;           /* --N: global grid is N^3, domain is the unit cube */
+  uint32_t model;       /* MPM_MODEL_* */
+  uint32_t svd_mode;    /* MPM_SVD_* */
+  uint32_t sort_every;  /* re-bin (sort + permute) every this many substeps; 0 = never after upload */
+  uint32_t x_begin;     /* slab decomposition: first owned x-plane (0 for a single device) */
+  uint32_t x_end;       /* one past the last owned x-plane (N for a single device; 0 means N) */
+  int32_t device;       /* CUDA device ordinal, -1 = current */
+  uint64_t capacity;    /* particle slots to allocate (0 = size of the first upload) */
+} MpmParams;
+
+typedef struct MpmSim MpmSim;
+
+/* MaterialModel constructor arithmetic (MaterialModel.cuh:26-29, 50-54, 74-84 as called from
+ * src/main.cu:36-42); host only */
+void mpm_make_material(double volume, double density, double E, double Nu, double hardening,
+                       double plast_clamp_lower, double plast_clamp_higher, MpmMaterial* out);
+
+/* Simulation::Simulation + initCuda() minus the particle upload (src/mpm.cu:180-207) */
+int mpm_create(const MpmParams* params, const MpmMaterial* materials, int n_materials, MpmSim** out);
+/* Simulation::~Simulation (src/mpm.cu:190-195) */
+void mpm_destroy(MpmSim* sim);
+const char* mpm_last_error(const MpmSim* sim); /* sim may be NULL: last creation error */
+int mpm_abi_version(void);
+
+/* particlesToDevice (src/mpm.cu:278-286): host AoS -> device SoA; replaces the active set */
+int mpm_upload_particles_aos(MpmSim* sim, const MpmParticle* particles, size_t count);
+/* particlesToHost (src/mpm.cu:288-306): blocking; particles come back in upload order */
+int mpm_download_particles_aos(MpmSim* sim, MpmParticle* particles, size_t capacity, size_t* count);
+/* positions only (12 B/particle), upload order — what the reference's viewer cadence needs */
+int mpm_download_positions(MpmSim* sim, float* xyz, size_t capacity, size_t* count);
+/* synthetic dense block generated on the device: ids
+ * [first_id, first_id+count), x = lo + (hi-lo)*u(hash(seed,id,axis)), v=0, F=I, C=0, Jp=1;
+ * only particles whose base node lies in this handle's slab are kept */
+int mpm_generate_dense_block(MpmSim* sim, uint64_t first_id, uint64_t count, uint32_t seed, float lo, float hi,
+                             uint8_t material);
+size_t mpm_particle_count(const MpmSim* sim);
+
+/* Simulation::advance() x n_substeps (src/mpm.cu:323-329); asynchronous like the reference */
+int mpm_advance(MpmSim* sim, int n_substeps);
+/* block until the device is idle (what syncDevice's cudaMemcpy does implicitly, src/mpm.cu:289) */
+int mpm_sync(MpmSim* sim);
+double mpm_time(const MpmSim* sim);           /* Simulation::t */
+uint64_t mpm_substeps_done(const MpmSim* sim);
+uint64_t mpm_kernel_launches(const MpmSim* sim); /* kernels this handle has launched so far */
+
+/* single stages, for parity tests and profiling (same kernels mpm_advance runs) */
+int mpm_stage_sort(MpmSim* sim);        /* north-star stage (1): cell keys, radix sort, SoA permute */
+int mpm_stage_reset_grid(MpmSim* sim);  /* resetGrid, src/mpm.cu:213-215 */
+int mpm_stage_p2g(MpmSim* sim);         /* particleToGrid, src/mpm.cu:14-74 */
+int mpm_stage_grid_update(MpmSim* sim); /* gridOpKernel, src/mpm.cu:76-107 */
+int mpm_stage_g2p(MpmSim* sim);         /* gridToParticle, src/mpm.cu:109-178 */
+
+/* debug access to internal state (parity tests) */
+int mpm_debug_download_grid(MpmSim* sim, float* vec4, size_t n_nodes);       /* local slab incl. ghost planes */
+int mpm_debug_upload_grid(MpmSim* sim, const float* vec4, size_t n_nodes);
+int mpm_debug_download_sort(MpmSim* sim, uint32_t* keys, uint32_t* ids, size_t capacity); /* current order */
+size_t mpm_grid_nodes(const MpmSim* sim);
+
+/* accumulated CUDA-event time per stage since the last call (ms); enables timing on first call */
+int mpm_get_stage_times(MpmSim* sim, float ms[MPM_STAGE_COUNT]);
+/* stream the handle launches on (cudaStream_t), for callers that time with their own events */
+void* mpm_stream(MpmSim* sim);
+
+/* multi-GPU (one handle per rank, slabs along x): NCCL communicator from a unique id that the
+ * host launcher distributes (128 bytes, mpm_comm_unique_id on rank 0) */
+int mpm_comm_unique_id(void* id128);
+int mpm_attach_comm(MpmSim* sim, const void* id128, int rank, int nranks);
+
+/* linalg known-answer hooks (reference tests/test_linalg.cu:49-91): row-major 3x3 batches on the device */
+int mpm_svd3_batch(const float* A, float* U, float* S, float* V, size_t n, int svd_mode);
+int mpm_polar_batch(const float* A, float* R, size_t n, int svd_mode);
+int mpm_determinant_batch(const float* A, float* det, size_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPM_B200_H */

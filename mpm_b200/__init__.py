@@ -1,0 +1,10 @@
+"""mpm_b200 — B200-native MLS-MPM substep (drop-in for the hot path of kekeblom/mpm).
+
+The product is the CUDA library `libmpm_b200.so` behind the C ABI in include/mpm_b200.h; this
+package is the Python host-side mirror used by tests and bench.py.  There is no CPU fallback:
+loading fails loudly if the library is missing and creating a simulation fails without a GPU.
+"""
+from .api import (  # noqa: F401
+    FIXED_COROTATED, SNOW, SVD_EXACT, SVD_FAST, STAGES, PARTICLE_DTYPE, MpmError, Sim, lib, make_material,
+    svd3_batch, polar_batch, determinant_batch, comm_unique_id,
+)

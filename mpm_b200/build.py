@@ -1,0 +1,36 @@
+"""Builds mpm_b200/libmpm_b200.so (CUDA kernels + C ABI) in-tree for sm_100a with nvcc."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libmpm_b200.so")
+SOURCES = ["mpm_sim.cu"]
+
+
+def _newest_source():
+    t = 0.0
+    for root in (CSRC, os.path.join(os.path.dirname(HERE), "include")):
+        for f in os.listdir(root):
+            t = max(t, os.path.getmtime(os.path.join(root, f)))
+    return t
+
+
+def build(force=False, verbose=False):
+    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _newest_source():
+        return LIB
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-shared",
+           "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++", "-Xptxas", "-v" if verbose else "-warn-spills",
+           "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lnccl"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or r.returncode:
+        sys.stderr.write(r.stdout + r.stderr)
+    if r.returncode:
+        raise RuntimeError("nvcc failed building libmpm_b200.so")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force=True, verbose="-v" in sys.argv))

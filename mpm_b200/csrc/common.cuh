@@ -1,0 +1,119 @@
+// Shared device-side definitions: SoA particle streams, kernel parameters, material math.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mpm_b200.h"
+#include "svd3.cuh"
+
+namespace mpm {
+
+// ---- particle streams in HBM ------------------------------------------------------------------
+// 25 float streams (x3, v3, F9 row-major, C9 row-major, Jp), each `stride` floats long and
+// 128-byte aligned, so a warp reading stream s for 32 consecutive particles touches exactly one
+// 128 B line.  Plus u32 id (upload order, for un-permuting on download) and u8 material.
+enum : int { SX = 0, SV = 3, SF = 6, SC = 15, SJ = 24, NSTREAM = 25 };
+
+struct Soa {
+  float* f;       // NSTREAM * stride floats
+  uint32_t* id;   // stride
+  uint8_t* mat;   // stride
+  size_t stride;  // multiple of 32
+  __host__ __device__ __forceinline__ float* s(int stream) const { return f + (size_t)stream * stride; }
+};
+
+// replaces SimulationParameters (reference include/TransferScheme.h:6-29) on the device
+struct KParams {
+  float dt;
+  float dx;      // (float)(1.0 / N)
+  float dx_inv;  // (float)(1.0 / (double)dx)  -- not exactly N for non powers of two
+  float dinv;    // (4 * dx_inv) * dx_inv : the diagonal of D^-1 (InterpolationKernel.cuh:71-73)
+  int N;
+  int x0;   // first x-plane held in the local grid
+  int nxl;  // x-planes held locally (owned + ghost)
+  int x_own_begin, x_own_end;
+};
+
+__device__ __forceinline__ float clampf(float x, float lo, float hi) { return fmaxf(fminf(x, hi), lo); }
+
+// quadratic B-spline weights and base node (reference include/InterpolationKernel.cuh:57-69);
+// base uses C truncation like the reference's cast<int>()
+__device__ __forceinline__ void bspline(float x, float dx_inv, int& base, float& fx, float w[3]) {
+  const float g = x * dx_inv;
+  base = (int)(g - 0.5f);
+  fx = g - (float)base;
+  const float d0 = 1.5f - fx, d1 = fx - 1.0f, d2 = fx - 0.5f;
+  w[0] = 0.5f * (d0 * d0);
+  w[1] = 0.75f - (d1 * d1);
+  w[2] = 0.5f * (d2 * d2);
+}
+
+__device__ __forceinline__ MpmMaterial load_material(const MpmMaterial* __restrict__ mats, int idx) {
+  const float* p = reinterpret_cast<const float*>(mats + idx);
+  MpmMaterial m;
+  m.particleVolume = __ldg(p + 0);
+  m.particleMass = __ldg(p + 1);
+  m.mu0 = __ldg(p + 2);
+  m.lambda0 = __ldg(p + 3);
+  m.hardening = __ldg(p + 4);
+  m.plast_clamp_lower = __ldg(p + 5);
+  m.plast_clamp_higher = __ldg(p + 6);
+  return m;
+}
+
+// P(F) F^T of the fixed-corotated model with snow hardening
+// (reference MMSnow::computePF, include/MaterialModel.cuh:85-93; MMFixedCorotated :56-61).
+// "J" is the plastic scalar Jp, as in the reference.  EXACT evaluates exp and the lambda term
+// in double like the reference; FAST stays in f32 and skips exp when hardening == 0.
+template <int MODEL, class O, bool EXACT>
+__device__ __forceinline__ Mat3 compute_PF(const Mat3& F, float Jp, const MpmMaterial& m) {
+  const Mat3 R = polar_rotation<O>(F);
+  float mu = m.mu0, lambda = m.lambda0;
+  if (MODEL == MPM_MODEL_SNOW) {
+    float e;
+    if (EXACT) {
+      e = (float)exp((double)m.hardening * (1.0 - (double)Jp));
+    } else {
+      e = (m.hardening == 0.0f) ? 1.0f : __expf(m.hardening * (1.0f - Jp));
+    }
+    mu *= e;
+    lambda *= e;
+  }
+  const float two_mu = 2.0f * mu;
+  float lam_term;
+  if (EXACT) {
+    lam_term = (float)((double)lambda * (((double)Jp - 1.0) * (double)Jp));
+  } else {
+    lam_term = lambda * ((Jp - 1.0f) * Jp);
+  }
+  Mat3 D;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) D.m[i][j] = two_mu * (F.m[i][j] - R.m[i][j]);
+  Mat3 PF = mul_abt(D, F);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) PF.m[i][i] += lam_term;
+  return PF;
+}
+
+// snow plasticity (reference MMSnow::endOfStepMutation, include/MaterialModel.cuh:95-114)
+template <class O>
+__device__ __forceinline__ void snow_plasticity(Mat3& F, float& Jp, const MpmMaterial& m) {
+  Mat3 U, V;
+  float sig[3];
+  svd3<O>(F, U, sig, V);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) sig[i] = clampf(sig[i], m.plast_clamp_lower, m.plast_clamp_higher);
+  const float oldJ = det3(F);
+  Mat3 US;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) US.m[i][j] = U.m[i][j] * sig[j];
+  F = mul_abt(US, V);
+  const float Fdet = det3(F);
+  Jp = clampf(Jp * oldJ / Fdet, 0.6f, 20.0f);
+}
+
+}  // namespace mpm

@@ -1,0 +1,583 @@
+// C ABI of the B200-native MLS-MPM substep: handle, buffers, stage launches.
+// Replaces the device side of the reference's Simulation class (src/mpm.cu:180-329).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/mpm_b200.h"
+#include "comm.cuh"
+#include "kernels.cuh"
+#include "sort.cuh"
+
+using namespace mpm;
+
+static thread_local std::string g_create_error;
+
+struct MpmSim {
+  MpmParams par{};
+  KParams k{};
+  int device = 0;
+  cudaStream_t stream = nullptr;
+
+  // particles: two SoA buffers (sort permutes from one into the other)
+  Soa soa[2]{};
+  int cur = 0;
+  size_t capacity = 0;
+  size_t count = 0;
+  uint32_t first_id = 0;
+
+  // grid: nxl * N * N float4
+  float4* grid = nullptr;
+  size_t grid_nodes = 0;
+
+  MpmMaterial* mats = nullptr;
+  int n_mats = 0;
+
+  // sort scratch
+  uint32_t* keys[2] = {nullptr, nullptr};
+  uint32_t* vals[2] = {nullptr, nullptr};
+  uint32_t* table = nullptr;
+  size_t table_len = 0;
+  uint32_t* scan_sums = nullptr;
+  size_t scan_sums_len = 0;
+  int key_bits = 0;
+  int sorted_cur = 0;  // which keys[] buffer holds the keys of the current order
+
+  MpmParticle* aos_stage = nullptr;  // device AoS staging for upload/download
+  size_t aos_stage_cap = 0;
+  unsigned long long* d_counter = nullptr;
+
+  uint64_t substeps = 0;
+  uint64_t steps_since_sort = 0;
+  uint64_t launches = 0;
+  double t = 0.0;
+
+  bool timing = false;
+  cudaEvent_t ev[2]{};
+  float stage_ms[MPM_STAGE_COUNT]{};
+
+  Comm comm;
+  std::string err;
+};
+
+namespace {
+
+int fail(MpmSim* s, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (s) s->err = buf; else g_create_error = buf;
+  return 1;
+}
+
+#define CK(call)                                                                                    \
+  do {                                                                                              \
+    cudaError_t e_ = (call);                                                                        \
+    if (e_ != cudaSuccess) return fail(sim, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)) ? (int)e_ : (int)e_; \
+  } while (0)
+
+inline unsigned blocks_for(size_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+int alloc_soa(MpmSim* sim, Soa& s, size_t cap) {
+  s.stride = (cap + 31) / 32 * 32;
+  CK(cudaMalloc(&s.f, sizeof(float) * NSTREAM * s.stride));
+  CK(cudaMalloc(&s.id, sizeof(uint32_t) * s.stride));
+  CK(cudaMalloc(&s.mat, s.stride));
+  return 0;
+}
+void free_soa(Soa& s) {
+  cudaFree(s.f);
+  cudaFree(s.id);
+  cudaFree(s.mat);
+  s = Soa{};
+}
+
+int ensure_capacity(MpmSim* sim, size_t cap) {
+  if (cap <= sim->capacity) return 0;
+  if (sim->capacity != 0) {
+    for (int b = 0; b < 2; ++b) free_soa(sim->soa[b]);
+    for (int b = 0; b < 2; ++b) {
+      cudaFree(sim->keys[b]);
+      cudaFree(sim->vals[b]);
+    }
+    cudaFree(sim->table);
+    cudaFree(sim->scan_sums);
+  }
+  for (int b = 0; b < 2; ++b) {
+    if (int rc = alloc_soa(sim, sim->soa[b], cap)) return rc;
+    CK(cudaMalloc(&sim->keys[b], sizeof(uint32_t) * cap));
+    CK(cudaMalloc(&sim->vals[b], sizeof(uint32_t) * cap));
+  }
+  const size_t n_tiles = (cap + kSortTile - 1) / kSortTile;
+  sim->table_len = n_tiles * kRadix;
+  CK(cudaMalloc(&sim->table, sizeof(uint32_t) * sim->table_len));
+  sim->scan_sums_len = (sim->table_len + kScanTile - 1) / kScanTile;
+  CK(cudaMalloc(&sim->scan_sums, sizeof(uint32_t) * sim->scan_sums_len));
+  sim->capacity = cap;
+  return 0;
+}
+
+int ensure_stage(MpmSim* sim, size_t n) {
+  if (n <= sim->aos_stage_cap) return 0;
+  cudaFree(sim->aos_stage);
+  sim->aos_stage = nullptr;
+  sim->aos_stage_cap = 0;
+  CK(cudaMalloc(&sim->aos_stage, sizeof(MpmParticle) * n));
+  sim->aos_stage_cap = n;
+  return 0;
+}
+
+struct StageTimer {
+  MpmSim* s;
+  int stage;
+  StageTimer(MpmSim* s_, int st) : s(s_), stage(st) {
+    if (s->timing) cudaEventRecord(s->ev[0], s->stream);
+  }
+  ~StageTimer() {
+    if (s->timing) {
+      cudaEventRecord(s->ev[1], s->stream);
+      cudaEventSynchronize(s->ev[1]);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]);
+      s->stage_ms[stage] += ms;
+    }
+  }
+};
+
+// ---- stages -------------------------------------------------------------------------------------
+int do_sort(MpmSim* sim) {
+  StageTimer tm(sim, MPM_STAGE_SORT);
+  const size_t n = sim->count;
+  sim->steps_since_sort = 0;
+  if (n == 0) return 0;
+  Soa& src = sim->soa[sim->cur];
+  cell_key_kernel<<<blocks_for(n, 256), 256, 0, sim->stream>>>(src, n, sim->k, sim->keys[0], sim->vals[0]);
+  sim->launches++;
+  const int n_tiles = (int)((n + kSortTile - 1) / kSortTile);
+  const size_t table_len = (size_t)n_tiles * kRadix;
+  const unsigned scan_blocks = blocks_for(table_len, kScanTile);
+  int in = 0;
+  for (int shift = 0; shift < sim->key_bits; shift += kRadixBits) {
+    radix_hist_kernel<<<n_tiles, kSortThreads, 0, sim->stream>>>(sim->keys[in], n, shift, sim->table, n_tiles);
+    scan_tile_sums_kernel<<<scan_blocks, kScanThreads, 0, sim->stream>>>(sim->table, table_len, sim->scan_sums);
+    scan_sums_kernel<<<1, 1024, 0, sim->stream>>>(sim->scan_sums, scan_blocks);
+    scan_downsweep_kernel<<<scan_blocks, kScanThreads, 0, sim->stream>>>(sim->table, table_len, sim->scan_sums);
+    radix_scatter_kernel<<<n_tiles, kSortThreads, 0, sim->stream>>>(sim->keys[in], sim->vals[in], sim->keys[in ^ 1],
+                                                                     sim->vals[in ^ 1], n, shift, sim->table, n_tiles);
+    sim->launches += 5;
+    in ^= 1;
+  }
+  sim->sorted_cur = in;
+  Soa& dst = sim->soa[sim->cur ^ 1];
+  permute_kernel<<<blocks_for(n, 256), 256, 0, sim->stream>>>(src, dst, sim->vals[in], n);
+  sim->launches++;
+  sim->cur ^= 1;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int do_reset(MpmSim* sim) {
+  StageTimer tm(sim, MPM_STAGE_RESET);
+  CK(cudaMemsetAsync(sim->grid, 0, sizeof(float4) * sim->grid_nodes, sim->stream));
+  return 0;
+}
+
+template <int MODEL>
+int launch_p2g(MpmSim* sim) {
+  const size_t n = sim->count;
+  const unsigned nb = blocks_for(n, kParticleBlock);
+  Soa& p = sim->soa[sim->cur];
+  if (sim->par.svd_mode == MPM_SVD_EXACT)
+    p2g_kernel<MODEL, ExactOps, true><<<nb, kParticleBlock, 0, sim->stream>>>(p, n, sim->mats, sim->grid, sim->k);
+  else
+    p2g_kernel<MODEL, FastOps, false><<<nb, kParticleBlock, 0, sim->stream>>>(p, n, sim->mats, sim->grid, sim->k);
+  return 0;
+}
+int do_p2g(MpmSim* sim) {
+  StageTimer tm(sim, MPM_STAGE_P2G);
+  if (sim->count == 0) return 0;
+  if (sim->par.model == MPM_MODEL_SNOW) launch_p2g<MPM_MODEL_SNOW>(sim); else launch_p2g<MPM_MODEL_FIXED_COROTATED>(sim);
+  sim->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int do_grid(MpmSim* sim) {
+  StageTimer tm(sim, MPM_STAGE_GRID);
+  const size_t nodes = sim->grid_nodes;
+  grid_update_kernel<<<blocks_for(nodes, 256), 256, 0, sim->stream>>>(sim->grid, sim->k, 0, sim->k.nxl);
+  sim->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+template <int MODEL>
+int launch_g2p(MpmSim* sim) {
+  const size_t n = sim->count;
+  const unsigned nb = blocks_for(n, kParticleBlock);
+  Soa& p = sim->soa[sim->cur];
+  if (sim->par.svd_mode == MPM_SVD_EXACT)
+    g2p_kernel<MODEL, ExactOps><<<nb, kParticleBlock, 0, sim->stream>>>(p, n, sim->mats, sim->grid, sim->k);
+  else
+    g2p_kernel<MODEL, FastOps><<<nb, kParticleBlock, 0, sim->stream>>>(p, n, sim->mats, sim->grid, sim->k);
+  return 0;
+}
+int do_g2p(MpmSim* sim) {
+  StageTimer tm(sim, MPM_STAGE_G2P);
+  if (sim->count == 0) return 0;
+  if (sim->par.model == MPM_MODEL_SNOW) launch_g2p<MPM_MODEL_SNOW>(sim); else launch_g2p<MPM_MODEL_FIXED_COROTATED>(sim);
+  sim->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int bits_for(size_t n) {
+  int b = 1;
+  while (((size_t)1 << b) < n) ++b;
+  return b;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mpm_abi_version(void) { return MPM_B200_ABI_VERSION; }
+
+void mpm_make_material(double volume, double density, double E, double Nu, double hardening, double lo, double hi,
+                       MpmMaterial* out) {
+  // arguments arrive as doubles from the TOML reader and are narrowed to real at the call, then
+  // the constructor arithmetic runs in f32 (int literals promote to float)
+  const float vol = (float)volume, rho = (float)density, e = (float)E, nu = (float)Nu;
+  out->particleVolume = vol;
+  out->particleMass = rho * vol;
+  out->mu0 = e / (2 * (1 + nu));
+  out->lambda0 = e * nu / ((1 + nu) * (1 - 2 * nu));
+  out->hardening = (float)hardening;
+  out->plast_clamp_lower = (float)lo;
+  out->plast_clamp_higher = (float)hi;
+}
+
+int mpm_create(const MpmParams* params, const MpmMaterial* materials, int n_materials, MpmSim** out) {
+  MpmSim* sim = nullptr;
+  if (!params || !out) return fail(nullptr, "mpm_create: null argument");
+  if (params->N < 4) return fail(nullptr, "mpm_create: N must be >= 4");
+  if (n_materials < 1 || n_materials > 256 || !materials) return fail(nullptr, "mpm_create: need 1..256 materials");
+  if (params->model > MPM_MODEL_FIXED_COROTATED || params->svd_mode > MPM_SVD_FAST)
+    return fail(nullptr, "mpm_create: bad model / svd_mode");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, "mpm_create: no CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e));
+  sim = new (std::nothrow) MpmSim();
+  if (!sim) return fail(nullptr, "mpm_create: out of host memory");
+  sim->par = *params;
+  if (params->device >= 0) {
+    sim->device = params->device;
+  } else {
+    cudaGetDevice(&sim->device);
+  }
+#define CKC(call)                                                                          \
+  do {                                                                                     \
+    cudaError_t e_ = (call);                                                               \
+    if (e_ != cudaSuccess) {                                                               \
+      fail(nullptr, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));   \
+      mpm_destroy(sim);                                                                    \
+      return (int)e_;                                                                      \
+    }                                                                                      \
+  } while (0)
+  CKC(cudaSetDevice(sim->device));
+  cudaDeviceProp prop;
+  CKC(cudaGetDeviceProperties(&prop, sim->device));
+  if (prop.major < 10) {
+    fail(nullptr, "mpm_create: device %d is sm_%d%d; this library is built for sm_100a only", sim->device, prop.major, prop.minor);
+    mpm_destroy(sim);
+    return 1;
+  }
+  const int N = (int)params->N;
+  const int xb = (int)params->x_begin;
+  const int xe = params->x_end ? (int)params->x_end : N;
+  if (xb >= xe || xe > N) {
+    fail(nullptr, "mpm_create: bad slab [%d,%d) for N=%d", xb, xe, N);
+    mpm_destroy(sim);
+    return 1;
+  }
+  KParams& k = sim->k;
+  k.dt = params->dt;
+  k.N = N;
+  k.dx = (float)(1.0 / (double)N);
+  k.dx_inv = (float)(1.0 / (double)k.dx);
+  k.dinv = (4.0f * k.dx_inv) * k.dx_inv;
+  k.x_own_begin = xb;
+  k.x_own_end = xe;
+  k.x0 = xb;
+  k.nxl = std::min(N, xe + 2) - xb;  // owned planes + up to 2 ghost planes above
+  sim->grid_nodes = (size_t)k.nxl * N * N;
+  sim->key_bits = bits_for(sim->grid_nodes);
+  CKC(cudaStreamCreateWithFlags(&sim->stream, cudaStreamNonBlocking));
+  CKC(cudaEventCreate(&sim->ev[0]));
+  CKC(cudaEventCreate(&sim->ev[1]));
+  CKC(cudaMalloc(&sim->grid, sizeof(float4) * sim->grid_nodes));
+  CKC(cudaMemsetAsync(sim->grid, 0, sizeof(float4) * sim->grid_nodes, sim->stream));
+  sim->n_mats = n_materials;
+  CKC(cudaMalloc(&sim->mats, sizeof(MpmMaterial) * n_materials));
+  CKC(cudaMemcpy(sim->mats, materials, sizeof(MpmMaterial) * n_materials, cudaMemcpyHostToDevice));
+  CKC(cudaMalloc(&sim->d_counter, sizeof(unsigned long long)));
+  if (params->capacity) {
+    if (int rc = ensure_capacity(sim, (size_t)params->capacity)) {
+      g_create_error = sim->err;
+      mpm_destroy(sim);
+      return rc;
+    }
+  }
+#undef CKC
+  *out = sim;
+  return 0;
+}
+
+void mpm_destroy(MpmSim* sim) {
+  if (!sim) return;
+  cudaSetDevice(sim->device);
+  if (sim->stream) cudaStreamSynchronize(sim->stream);
+  sim->comm.destroy();
+  for (int b = 0; b < 2; ++b) {
+    free_soa(sim->soa[b]);
+    cudaFree(sim->keys[b]);
+    cudaFree(sim->vals[b]);
+  }
+  cudaFree(sim->table);
+  cudaFree(sim->scan_sums);
+  cudaFree(sim->grid);
+  cudaFree(sim->mats);
+  cudaFree(sim->aos_stage);
+  cudaFree(sim->d_counter);
+  if (sim->ev[0]) cudaEventDestroy(sim->ev[0]);
+  if (sim->ev[1]) cudaEventDestroy(sim->ev[1]);
+  if (sim->stream) cudaStreamDestroy(sim->stream);
+  delete sim;
+}
+
+const char* mpm_last_error(const MpmSim* sim) { return sim ? sim->err.c_str() : g_create_error.c_str(); }
+
+int mpm_upload_particles_aos(MpmSim* sim, const MpmParticle* particles, size_t count) {
+  if (!sim || (!particles && count)) return fail(sim, "mpm_upload_particles_aos: null argument");
+  CK(cudaSetDevice(sim->device));
+  if (int rc = ensure_capacity(sim, std::max<size_t>(count, 1))) return rc;
+  if (int rc = ensure_stage(sim, std::max<size_t>(count, 1))) return rc;
+  sim->count = count;
+  sim->first_id = 0;
+  sim->cur = 0;
+  if (count) {
+    CK(cudaMemcpyAsync(sim->aos_stage, particles, sizeof(MpmParticle) * count, cudaMemcpyHostToDevice, sim->stream));
+    aos_to_soa_kernel<<<blocks_for(count, 256), 256, 0, sim->stream>>>(sim->aos_stage, sim->soa[0], count, 0);
+    sim->launches++;
+    CK(cudaGetLastError());
+  }
+  // bin immediately: the substep kernels assume cell-sorted order for locality
+  return do_sort(sim);
+}
+
+int mpm_download_particles_aos(MpmSim* sim, MpmParticle* particles, size_t capacity, size_t* count) {
+  if (!sim) return 1;
+  CK(cudaSetDevice(sim->device));
+  if (count) *count = sim->count;
+  if (capacity < sim->count) return fail(sim, "mpm_download_particles_aos: capacity %zu < %zu", capacity, sim->count);
+  if (sim->count == 0) return 0;
+  if (int rc = ensure_stage(sim, sim->count)) return rc;
+  soa_to_aos_kernel<<<blocks_for(sim->count, 256), 256, 0, sim->stream>>>(sim->soa[sim->cur], sim->count, sim->aos_stage, sim->first_id);
+  sim->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(particles, sim->aos_stage, sizeof(MpmParticle) * sim->count, cudaMemcpyDeviceToHost, sim->stream));
+  CK(cudaStreamSynchronize(sim->stream));
+  return 0;
+}
+
+int mpm_download_positions(MpmSim* sim, float* xyz, size_t capacity, size_t* count) {
+  if (!sim) return 1;
+  CK(cudaSetDevice(sim->device));
+  if (count) *count = sim->count;
+  if (capacity < sim->count) return fail(sim, "mpm_download_positions: capacity too small");
+  if (sim->count == 0) return 0;
+  if (int rc = ensure_stage(sim, (sim->count * 12 + sizeof(MpmParticle) - 1) / sizeof(MpmParticle))) return rc;
+  float* stage = reinterpret_cast<float*>(sim->aos_stage);
+  positions_kernel<<<blocks_for(sim->count, 256), 256, 0, sim->stream>>>(sim->soa[sim->cur], sim->count, stage, sim->first_id);
+  sim->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(xyz, stage, sizeof(float) * 3 * sim->count, cudaMemcpyDeviceToHost, sim->stream));
+  CK(cudaStreamSynchronize(sim->stream));
+  return 0;
+}
+
+int mpm_generate_dense_block(MpmSim* sim, uint64_t first_id, uint64_t count, uint32_t seed, float lo, float hi, uint8_t material) {
+  if (!sim) return 1;
+  CK(cudaSetDevice(sim->device));
+  const bool whole = (sim->k.x_own_begin == 0 && sim->k.x_own_end == sim->k.N);
+  if (whole) {
+    if (int rc = ensure_capacity(sim, std::max<uint64_t>(count, 1))) return rc;
+  } else if (sim->capacity == 0) {
+    return fail(sim, "mpm_generate_dense_block: slab handles need MpmParams.capacity");
+  }
+  sim->cur = 0;
+  sim->first_id = (uint32_t)first_id;
+  CK(cudaMemsetAsync(sim->d_counter, 0, sizeof(unsigned long long), sim->stream));
+  if (count) {
+    generate_block_kernel<<<blocks_for(count, 256), 256, 0, sim->stream>>>(sim->soa[0], first_id, count, lowbias32(seed), lo, hi,
+                                                                            material, sim->k, whole, sim->d_counter, sim->capacity);
+    sim->launches++;
+    CK(cudaGetLastError());
+  }
+  if (whole) {
+    sim->count = count;
+  } else {
+    unsigned long long n = 0;
+    CK(cudaMemcpyAsync(&n, sim->d_counter, sizeof(n), cudaMemcpyDeviceToHost, sim->stream));
+    CK(cudaStreamSynchronize(sim->stream));
+    if (n > sim->capacity) return fail(sim, "mpm_generate_dense_block: %llu particles exceed capacity %zu", n, sim->capacity);
+    sim->count = (size_t)n;
+  }
+  return do_sort(sim);
+}
+
+size_t mpm_particle_count(const MpmSim* sim) { return sim ? sim->count : 0; }
+size_t mpm_grid_nodes(const MpmSim* sim) { return sim ? sim->grid_nodes : 0; }
+double mpm_time(const MpmSim* sim) { return sim ? sim->t : 0.0; }
+uint64_t mpm_substeps_done(const MpmSim* sim) { return sim ? sim->substeps : 0; }
+uint64_t mpm_kernel_launches(const MpmSim* sim) { return sim ? sim->launches : 0; }
+void* mpm_stream(MpmSim* sim) { return sim ? (void*)sim->stream : nullptr; }
+
+int mpm_stage_sort(MpmSim* sim) { if (!sim) return 1; CK(cudaSetDevice(sim->device)); return do_sort(sim); }
+int mpm_stage_reset_grid(MpmSim* sim) { if (!sim) return 1; CK(cudaSetDevice(sim->device)); return do_reset(sim); }
+int mpm_stage_p2g(MpmSim* sim) { if (!sim) return 1; CK(cudaSetDevice(sim->device)); return do_p2g(sim); }
+int mpm_stage_grid_update(MpmSim* sim) { if (!sim) return 1; CK(cudaSetDevice(sim->device)); return do_grid(sim); }
+int mpm_stage_g2p(MpmSim* sim) { if (!sim) return 1; CK(cudaSetDevice(sim->device)); return do_g2p(sim); }
+
+int mpm_advance(MpmSim* sim, int n_substeps) {
+  if (!sim) return 1;
+  CK(cudaSetDevice(sim->device));
+  for (int s = 0; s < n_substeps; ++s) {
+    if (sim->par.sort_every && sim->steps_since_sort >= sim->par.sort_every) {
+      if (int rc = do_sort(sim)) return rc;
+    }
+    if (int rc = do_reset(sim)) return rc;
+    if (int rc = do_p2g(sim)) return rc;
+    if (sim->comm.active()) {
+      StageTimer tm(sim, MPM_STAGE_EXCHANGE);
+      if (int rc = sim->comm.exchange_halo(sim->grid, sim->k, sim->stream, &sim->launches)) return fail(sim, "halo exchange failed: %s", sim->comm.error());
+    }
+    if (int rc = do_grid(sim)) return rc;
+    if (int rc = do_g2p(sim)) return rc;
+    sim->t += (double)sim->par.dt;
+    sim->substeps++;
+    sim->steps_since_sort++;
+  }
+  return 0;
+}
+
+int mpm_sync(MpmSim* sim) {
+  if (!sim) return 1;
+  CK(cudaSetDevice(sim->device));
+  CK(cudaStreamSynchronize(sim->stream));
+  return 0;
+}
+
+int mpm_debug_download_grid(MpmSim* sim, float* vec4, size_t n_nodes) {
+  if (!sim || !vec4) return 1;
+  CK(cudaSetDevice(sim->device));
+  if (n_nodes != sim->grid_nodes) return fail(sim, "grid has %zu nodes, caller passed %zu", sim->grid_nodes, n_nodes);
+  CK(cudaMemcpyAsync(vec4, sim->grid, sizeof(float4) * n_nodes, cudaMemcpyDeviceToHost, sim->stream));
+  CK(cudaStreamSynchronize(sim->stream));
+  return 0;
+}
+int mpm_debug_upload_grid(MpmSim* sim, const float* vec4, size_t n_nodes) {
+  if (!sim || !vec4) return 1;
+  CK(cudaSetDevice(sim->device));
+  if (n_nodes != sim->grid_nodes) return fail(sim, "grid has %zu nodes, caller passed %zu", sim->grid_nodes, n_nodes);
+  CK(cudaMemcpyAsync(sim->grid, vec4, sizeof(float4) * n_nodes, cudaMemcpyHostToDevice, sim->stream));
+  CK(cudaStreamSynchronize(sim->stream));
+  return 0;
+}
+int mpm_debug_download_sort(MpmSim* sim, uint32_t* keys, uint32_t* ids, size_t capacity) {
+  if (!sim) return 1;
+  CK(cudaSetDevice(sim->device));
+  if (capacity < sim->count) return fail(sim, "capacity too small");
+  if (sim->count == 0) return 0;
+  if (keys) CK(cudaMemcpyAsync(keys, sim->keys[sim->sorted_cur], sizeof(uint32_t) * sim->count, cudaMemcpyDeviceToHost, sim->stream));
+  if (ids) CK(cudaMemcpyAsync(ids, sim->soa[sim->cur].id, sizeof(uint32_t) * sim->count, cudaMemcpyDeviceToHost, sim->stream));
+  CK(cudaStreamSynchronize(sim->stream));
+  return 0;
+}
+
+int mpm_get_stage_times(MpmSim* sim, float ms[MPM_STAGE_COUNT]) {
+  if (!sim) return 1;
+  sim->timing = true;
+  for (int i = 0; i < MPM_STAGE_COUNT; ++i) {
+    if (ms) ms[i] = sim->stage_ms[i];
+    sim->stage_ms[i] = 0.f;
+  }
+  return 0;
+}
+
+int mpm_comm_unique_id(void* id128) { return Comm::unique_id(id128); }
+int mpm_attach_comm(MpmSim* sim, const void* id128, int rank, int nranks) {
+  if (!sim) return 1;
+  CK(cudaSetDevice(sim->device));
+  if (int rc = sim->comm.init(id128, rank, nranks, sim->k, sim->stream)) return fail(sim, "mpm_attach_comm: %s", sim->comm.error());
+  return 0;
+}
+
+// ---- linalg hooks ---------------------------------------------------------------------------------
+static int linalg_run(const float* A, size_t n, int mode, int what, float* o0, float* o1, float* o2) {
+  MpmSim* sim = nullptr;
+  float *dA = nullptr, *d0 = nullptr, *d1 = nullptr, *d2 = nullptr;
+  const size_t sz0 = (what == 2) ? n : 9 * n;
+  CK(cudaMalloc(&dA, sizeof(float) * 9 * n));
+  CK(cudaMalloc(&d0, sizeof(float) * sz0));
+  if (what == 0) {
+    CK(cudaMalloc(&d1, sizeof(float) * 3 * n));
+    CK(cudaMalloc(&d2, sizeof(float) * 9 * n));
+  }
+  CK(cudaMemcpy(dA, A, sizeof(float) * 9 * n, cudaMemcpyHostToDevice));
+  const unsigned nb = blocks_for(n, 128);
+  if (what == 0) {
+    if (mode == MPM_SVD_EXACT) svd3_batch_kernel<ExactOps><<<nb, 128>>>(dA, d0, d1, d2, n);
+    else svd3_batch_kernel<FastOps><<<nb, 128>>>(dA, d0, d1, d2, n);
+  } else if (what == 1) {
+    if (mode == MPM_SVD_EXACT) polar_batch_kernel<ExactOps><<<nb, 128>>>(dA, d0, n);
+    else polar_batch_kernel<FastOps><<<nb, 128>>>(dA, d0, n);
+  } else {
+    det_batch_kernel<<<nb, 128>>>(dA, d0, n);
+  }
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(o0, d0, sizeof(float) * sz0, cudaMemcpyDeviceToHost));
+  if (what == 0) {
+    CK(cudaMemcpy(o1, d1, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(o2, d2, sizeof(float) * 9 * n, cudaMemcpyDeviceToHost));
+  }
+  cudaFree(dA);
+  cudaFree(d0);
+  cudaFree(d1);
+  cudaFree(d2);
+  return 0;
+}
+int mpm_svd3_batch(const float* A, float* U, float* S, float* V, size_t n, int svd_mode) {
+  if (!n) return 0;
+  return linalg_run(A, n, svd_mode, 0, U, S, V);
+}
+int mpm_polar_batch(const float* A, float* R, size_t n, int svd_mode) {
+  if (!n) return 0;
+  return linalg_run(A, n, svd_mode, 1, R, nullptr, nullptr);
+}
+int mpm_determinant_batch(const float* A, float* det, size_t n) {
+  if (!n) return 0;
+  return linalg_run(A, n, 0, 2, det, nullptr, nullptr);
+}
+
+}  // extern "C"

@@ -1,0 +1,200 @@
+// Stage (1): particle cell binning — cell keys, stable LSD radix sort of (key, index) pairs, SoA
+// permute.  No reference counterpart (the reference never sorts); the contract is
+// the north star's: keys and permutation bit-exact against a stable sort on the key.
+//
+// Per 8-bit pass: (a) per-tile digit histogram, (b) exclusive scan of the digit-major table,
+// (c) scatter with a deterministic in-tile rank.  The rank is computed warp-synchronously with
+// match.any (peers holding the same digit) — no atomics decide an output position, so the
+// result is the unique stable permutation.
+#pragma once
+#include "common.cuh"
+
+namespace mpm {
+
+constexpr int kSortThreads = 256;
+constexpr int kSortWarps = kSortThreads / 32;
+constexpr int kSortItems = 8;                                     // keys per thread
+constexpr int kSortTile = kSortThreads * kSortItems;              // keys per block
+constexpr int kRadixBits = 8;
+constexpr int kRadix = 1 << kRadixBits;
+
+// key = N^2*bi + N*bj + bk of the clamped base node, bi local to the slab
+__global__ void cell_key_kernel(Soa p, size_t count, KParams k, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  int b[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    float fx, w[3];
+    bspline(p.s(SX + a)[i], k.dx_inv, b[a], fx, w);
+    b[a] = min(max(b[a], 0), k.N - 1);
+  }
+  const int bx = min(max(b[0] - k.x0, 0), k.nxl - 1);
+  keys[i] = (uint32_t)((bx * k.N + b[1]) * k.N + b[2]);
+  vals[i] = (uint32_t)i;
+}
+
+// (a) table[d * n_tiles + tile] = number of keys of this tile whose digit is d
+__global__ void __launch_bounds__(kSortThreads)
+radix_hist_kernel(const uint32_t* __restrict__ keys, size_t count, int shift, uint32_t* __restrict__ table, int n_tiles) {
+  __shared__ uint32_t h[kRadix];
+  for (int d = threadIdx.x; d < kRadix; d += kSortThreads) h[d] = 0;
+  __syncthreads();
+  const size_t tile0 = (size_t)blockIdx.x * kSortTile;
+#pragma unroll
+  for (int it = 0; it < kSortItems; ++it) {
+    const size_t i = tile0 + (size_t)it * kSortThreads + threadIdx.x;
+    if (i < count) atomicAdd(&h[(keys[i] >> shift) & (kRadix - 1)], 1u);
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < kRadix; d += kSortThreads) table[(size_t)d * n_tiles + blockIdx.x] = h[d];
+}
+
+// (b) device-wide exclusive scan of uint32, three launches: tile sums, scan of sums, downsweep
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* smem /*>= 32*/, uint32_t& total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) smem[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t s = (lane < (int)(blockDim.x >> 5)) ? smem[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, s, o);
+      if (lane >= o) s += t;
+    }
+    smem[lane] = s;
+  }
+  __syncthreads();
+  const uint32_t warp_off = warp ? smem[warp - 1] : 0;
+  total = smem[(blockDim.x >> 5) - 1];
+  __syncthreads();
+  return warp_off + inc - v;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_tile_sums_kernel(const uint32_t* __restrict__ in, size_t n, uint32_t* __restrict__ sums) {
+  __shared__ uint32_t sm[32];
+  const size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
+  uint32_t s = 0;
+#pragma unroll
+  for (int j = 0; j < kScanItems; ++j)
+    if (base + j < n) s += in[base + j];
+  uint32_t total;
+  block_exclusive_scan(s, sm, total);
+  if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+// single block: exclusive scan of `sums` in place (n up to a few 10^5)
+__global__ void __launch_bounds__(1024) scan_sums_kernel(uint32_t* sums, size_t n) {
+  __shared__ uint32_t sm[32];
+  uint32_t carry = 0;
+  for (size_t base = 0; base < n; base += 1024) {
+    const size_t i = base + threadIdx.x;
+    const uint32_t v = (i < n) ? sums[i] : 0;
+    uint32_t total;
+    const uint32_t ex = block_exclusive_scan(v, sm, total);
+    if (i < n) sums[i] = carry + ex;
+    carry += total;
+  }
+}
+__global__ void __launch_bounds__(kScanThreads) scan_downsweep_kernel(uint32_t* __restrict__ data, size_t n, const uint32_t* __restrict__ sums) {
+  __shared__ uint32_t sm[32];
+  const size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
+  uint32_t v[kScanItems];
+  uint32_t s = 0;
+#pragma unroll
+  for (int j = 0; j < kScanItems; ++j) {
+    v[j] = (base + j < n) ? data[base + j] : 0;
+    s += v[j];
+  }
+  uint32_t total;
+  uint32_t run = block_exclusive_scan(s, sm, total) + sums[blockIdx.x];
+#pragma unroll
+  for (int j = 0; j < kScanItems; ++j) {
+    if (base + j < n) data[base + j] = run;
+    run += v[j];
+  }
+}
+
+// (c) stable scatter.  Warp w owns the contiguous chunk [tile0 + w*256, +256) of its tile and
+// walks it 32 keys at a time, so (warp, iteration, lane) order is the input order.
+__global__ void __launch_bounds__(kSortThreads)
+radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ keys_out,
+                     uint32_t* __restrict__ vals_out, size_t count, int shift, const uint32_t* __restrict__ table, int n_tiles) {
+  __shared__ uint32_t cnt[kSortWarps][kRadix];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int d = threadIdx.x; d < kSortWarps * kRadix; d += kSortThreads) (&cnt[0][0])[d] = 0;
+  __syncthreads();
+  const size_t chunk0 = (size_t)blockIdx.x * kSortTile + (size_t)warp * (kSortItems * 32);
+  uint32_t key[kSortItems], val[kSortItems], rank[kSortItems];
+  const uint32_t lt_mask = (1u << lane) - 1u;
+#pragma unroll
+  for (int it = 0; it < kSortItems; ++it) {
+    const size_t i = chunk0 + (size_t)it * 32 + lane;
+    const bool valid = i < count;
+    key[it] = valid ? keys_in[i] : 0u;
+    val[it] = valid ? vals_in[i] : 0u;
+    const uint32_t digit = valid ? ((key[it] >> shift) & (kRadix - 1)) : (uint32_t)(kRadix + lane);
+    const uint32_t peers = __match_any_sync(0xffffffffu, digit);
+    const int leader = __ffs(peers) - 1;
+    uint32_t before = 0;
+    if (valid && lane == leader) {
+      before = cnt[warp][digit];
+      cnt[warp][digit] = before + __popc(peers);
+    }
+    before = __shfl_sync(0xffffffffu, before, leader);
+    rank[it] = before + __popc(peers & lt_mask);
+    __syncwarp();
+  }
+  __syncthreads();
+  // turn per-warp counts into output bases: global tile offset + counts of earlier warps
+  for (int d = threadIdx.x; d < kRadix; d += kSortThreads) {
+    uint32_t run = table[(size_t)d * n_tiles + blockIdx.x];
+#pragma unroll
+    for (int w = 0; w < kSortWarps; ++w) {
+      const uint32_t c = cnt[w][d];
+      cnt[w][d] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int it = 0; it < kSortItems; ++it) {
+    const size_t i = chunk0 + (size_t)it * 32 + lane;
+    if (i < count) {
+      const uint32_t digit = (key[it] >> shift) & (kRadix - 1);
+      const uint32_t pos = cnt[warp][digit] + rank[it];
+      keys_out[pos] = key[it];
+      vals_out[pos] = val[it];
+    }
+  }
+}
+
+// histogram tiles must match the scatter's tiles: tile t = keys [t*kSortTile, (t+1)*kSortTile)
+static_assert(kSortTile == kSortWarps * kSortItems * 32, "tile layout");
+
+// SoA permute: dst[r] = src[perm[r]] for every stream (+ id, material)
+__global__ void __launch_bounds__(256) permute_kernel(Soa src, Soa dst, const uint32_t* __restrict__ perm, size_t count) {
+  const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= count) return;
+  const uint32_t s = perm[r];
+  float t[NSTREAM];
+#pragma unroll
+  for (int q = 0; q < NSTREAM; ++q) t[q] = src.s(q)[s];
+  const uint32_t id = src.id[s];
+  const uint8_t mt = src.mat[s];
+#pragma unroll
+  for (int q = 0; q < NSTREAM; ++q) dst.s(q)[r] = t[q];
+  dst.id[r] = id;
+  dst.mat[r] = mt;
+}
+
+}  // namespace mpm

@@ -1,0 +1,348 @@
+// 3x3 SVD / polar decomposition / determinant for the MLS-MPM substep (sm_100a).
+//
+// Replaces the reference's include/svd3_cuda.h:35-1043 (McAdams et al. TR1690) and the wrappers
+// of src/linalg.cu:18-53.  Written from the algorithm, not from the reference's text: the Jacobi
+// conjugation and the QR Givens step are one routine each, applied with rotated roles.
+//
+// Two arithmetic policies:
+//   ExactOps — every product and sum individually rounded (__fmul_rn/__fadd_rn/__fsub_rn) and
+//              the correctly rounded __frsqrt_rn, i.e. exactly the operation sequence of the
+//              reference header.  Bit-identical to the reference svd3 (tests/test_gpu_linalg.py).
+//   FastOps  — plain operators (nvcc contracts to FFMA) and the MUFU.RSQ approximation.  Its
+//              deviation from ExactOps is a reported test result (<= a few 1e-7 on U, V).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace mpm {
+
+struct ExactOps {
+  static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+  static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+  static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+  static __device__ __forceinline__ float rsqrt(float x) { return __frsqrt_rn(x); }
+};
+struct FastOps {
+  static __device__ __forceinline__ float mul(float a, float b) { return a * b; }
+  static __device__ __forceinline__ float add(float a, float b) { return a + b; }
+  static __device__ __forceinline__ float sub(float a, float b) { return a - b; }
+  static __device__ __forceinline__ float rsqrt(float x) { return rsqrtf(x); }
+};
+
+struct Mat3 {
+  float m[3][3];  // row-major m[r][c]
+};
+
+namespace svd_detail {
+
+constexpr float kTiny = 1.e-20f;
+constexpr float kSmall = 1.e-12f;
+constexpr float kFourGammaSquared = 5.8284273147583007813f;  // (3 + 2*sqrt(2))
+constexpr unsigned kSinPi8 = 1053028117u;                    // bit patterns of sin/cos(pi/8)
+constexpr unsigned kCosPi8 = 1064076127u;
+
+// One approximate-Givens Jacobi conjugation of the symmetric S = A^T A in the plane whose
+// off-diagonal entry is s21 (s31/s32 couple the plane to the third axis), accumulating the
+// rotation into the quaternion (qx,qy,qz,qs).
+template <class O>
+__device__ __forceinline__ void jacobi(float& s11, float& s21, float& s31, float& s22, float& s32, float& s33,
+                                       float& qx, float& qy, float& qz, float& qs) {
+  float sh = O::mul(s21, 0.5f);
+  float t5 = O::sub(s11, s22);
+  float t2 = O::mul(sh, sh);
+  const bool nz = (t2 >= kTiny);
+  sh = nz ? sh : 0.0f;
+  float ch = nz ? t5 : 1.0f;
+  float t1 = O::mul(sh, sh);
+  t2 = O::mul(ch, ch);
+  float t3 = O::add(t1, t2);
+  float t4 = O::rsqrt(t3);
+  sh = O::mul(t4, sh);
+  ch = O::mul(t4, ch);
+  t1 = O::mul(kFourGammaSquared, t1);
+  const bool big = (t2 <= t1);
+  sh = big ? __uint_as_float(kSinPi8) : sh;
+  ch = big ? __uint_as_float(kCosPi8) : ch;
+  t1 = O::mul(sh, sh);
+  t2 = O::mul(ch, ch);
+  const float c = O::sub(t2, t1);
+  float s = O::mul(ch, sh);
+  s = O::add(s, s);
+  // S <- Q^T S Q
+  t3 = O::add(t1, t2);
+  s33 = O::mul(s33, t3);
+  s31 = O::mul(s31, t3);
+  s32 = O::mul(s32, t3);
+  s33 = O::mul(s33, t3);
+  t1 = O::mul(s, s31);
+  t2 = O::mul(s, s32);
+  s31 = O::mul(c, s31);
+  s32 = O::mul(c, s32);
+  s31 = O::add(t2, s31);
+  s32 = O::sub(s32, t1);
+  t2 = O::mul(s, s);
+  t1 = O::mul(s22, t2);
+  t3 = O::mul(s11, t2);
+  t4 = O::mul(c, c);
+  s11 = O::mul(s11, t4);
+  s22 = O::mul(s22, t4);
+  s11 = O::add(s11, t1);
+  s22 = O::add(s22, t3);
+  t4 = O::sub(t4, t2);
+  t2 = O::add(s21, s21);
+  s21 = O::mul(s21, t4);
+  t4 = O::mul(c, s);
+  t2 = O::mul(t2, t4);
+  t5 = O::mul(t5, t4);
+  s11 = O::add(s11, t2);
+  s21 = O::sub(s21, t5);
+  s22 = O::sub(s22, t2);
+  // q <- q * (ch, sh about the plane normal)
+  t1 = O::mul(sh, qx);
+  t2 = O::mul(sh, qy);
+  t3 = O::mul(sh, qz);
+  sh = O::mul(sh, qs);
+  qs = O::mul(ch, qs);
+  qx = O::mul(ch, qx);
+  qy = O::mul(ch, qy);
+  qz = O::mul(ch, qz);
+  qz = O::add(qz, sh);
+  qs = O::sub(qs, t3);
+  qx = O::add(qx, t2);
+  qy = O::sub(qy, t1);
+}
+
+template <class O>
+__device__ __forceinline__ float rsqrt_newton(float t2) {  // rsqrt + one Newton step
+  float t1 = O::rsqrt(t2);
+  const float t4 = O::mul(t1, 0.5f);
+  float t3 = O::mul(t1, t4);
+  t3 = O::mul(t1, t3);
+  t3 = O::mul(t2, t3);
+  t1 = O::add(t1, t4);
+  t1 = O::sub(t1, t3);
+  return t1;
+}
+
+template <class O>
+__device__ __forceinline__ void givens(float app, float aqp, float& c, float& s) {
+  float sh = O::mul(aqp, aqp);
+  sh = (sh >= kSmall) ? aqp : 0.0f;
+  float ch = O::sub(0.0f, app);
+  ch = fmaxf(ch, app);
+  ch = fmaxf(ch, kSmall);
+  const bool pos = (app >= 0.0f);
+  float t1 = O::mul(ch, ch);
+  float t2 = O::mul(sh, sh);
+  t2 = O::add(t1, t2);
+  t1 = rsqrt_newton<O>(t2);
+  t1 = O::mul(t1, t2);
+  ch = O::add(ch, t1);
+  const float ch0 = ch, sh0 = sh;
+  ch = pos ? ch0 : sh0;
+  sh = pos ? sh0 : ch0;
+  t1 = O::mul(ch, ch);
+  t2 = O::mul(sh, sh);
+  t2 = O::add(t1, t2);
+  t1 = rsqrt_newton<O>(t2);
+  ch = O::mul(ch, t1);
+  sh = O::mul(sh, t1);
+  c = O::mul(ch, ch);
+  s = O::mul(sh, sh);
+  c = O::sub(c, s);
+  s = O::mul(sh, ch);
+  s = O::add(s, s);
+}
+
+template <class O>
+__device__ __forceinline__ void rot(float c, float s, float& p, float& q) {
+  const float t1 = O::mul(s, p);
+  const float t2 = O::mul(s, q);
+  p = O::mul(c, p);
+  q = O::mul(c, q);
+  p = O::add(p, t2);
+  q = O::sub(q, t1);
+}
+
+__device__ __forceinline__ void swapf(float& a, float& b) {
+  const float t = a;
+  a = b;
+  b = t;
+}
+
+}  // namespace svd_detail
+
+// A = U diag(S) V^T, U and V rotations, |S0| >= |S1| >= |S2|, S2 carries the sign of det(A).
+template <class O>
+__device__ __forceinline__ void svd3(const Mat3& Ain, Mat3& U, float S[3], Mat3& V) {
+  using namespace svd_detail;
+  float a[3][3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) a[r][c] = Ain.m[r][c];
+
+  auto ata = [&](int i, int j) {
+    float r = O::mul(a[0][i], a[0][j]);
+    float t = O::mul(a[1][i], a[1][j]);
+    r = O::add(t, r);
+    t = O::mul(a[2][i], a[2][j]);
+    r = O::add(t, r);
+    return r;
+  };
+  float s11 = ata(0, 0), s21 = ata(1, 0), s31 = ata(2, 0), s22 = ata(1, 1), s32 = ata(2, 1), s33 = ata(2, 2);
+  float qs = 1.f, qx = 0.f, qy = 0.f, qz = 0.f;
+#pragma unroll 1
+  for (int sweep = 0; sweep < 4; ++sweep) {
+    jacobi<O>(s11, s21, s31, s22, s32, s33, qx, qy, qz, qs);
+    jacobi<O>(s22, s32, s21, s33, s31, s11, qy, qz, qx, qs);
+    jacobi<O>(s33, s31, s32, s11, s21, s22, qz, qx, qy, qs);
+  }
+  {  // normalise q
+    float t2 = O::mul(qs, qs);
+    float t1 = O::mul(qx, qx);
+    t2 = O::add(t1, t2);
+    t1 = O::mul(qy, qy);
+    t2 = O::add(t1, t2);
+    t1 = O::mul(qz, qz);
+    t2 = O::add(t1, t2);
+    t1 = rsqrt_newton<O>(t2);
+    qs = O::mul(qs, t1);
+    qx = O::mul(qx, t1);
+    qy = O::mul(qy, t1);
+    qz = O::mul(qz, t1);
+  }
+  float v[3][3];
+  {  // q -> V
+    const float x2 = O::mul(qx, qx), y2 = O::mul(qy, qy), z2 = O::mul(qz, qz);
+    float v11 = O::mul(qs, qs);
+    float v22 = O::sub(v11, x2);
+    float v33 = O::sub(v22, y2);
+    v33 = O::add(v33, z2);
+    v22 = O::add(v22, y2);
+    v22 = O::sub(v22, z2);
+    v11 = O::add(v11, x2);
+    v11 = O::sub(v11, y2);
+    v11 = O::sub(v11, z2);
+    const float dx2 = O::add(qx, qx), dy2 = O::add(qy, qy), dz2 = O::add(qz, qz);
+    float v32 = O::mul(qs, dx2);
+    float v13 = O::mul(qs, dy2);
+    float v21 = O::mul(qs, dz2);
+    const float p1 = O::mul(qy, dx2);
+    const float p2 = O::mul(qz, dy2);
+    const float p3 = O::mul(qx, dz2);
+    const float v12 = O::sub(p1, v21);
+    const float v23 = O::sub(p2, v32);
+    const float v31 = O::sub(p3, v13);
+    v21 = O::add(p1, v21);
+    v32 = O::add(p2, v32);
+    v13 = O::add(p3, v13);
+    v[0][0] = v11; v[0][1] = v12; v[0][2] = v13;
+    v[1][0] = v21; v[1][1] = v22; v[1][2] = v23;
+    v[2][0] = v31; v[2][1] = v32; v[2][2] = v33;
+  }
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {  // B = A V
+    const float a1 = a[r][0], a2 = a[r][1], a3 = a[r][2];
+    float b1 = O::mul(v[0][0], a1);
+    float b2 = O::mul(v[0][1], a1);
+    float b3 = O::mul(v[0][2], a1);
+    b1 = O::add(b1, O::mul(v[1][0], a2));
+    b1 = O::add(b1, O::mul(v[2][0], a3));
+    b2 = O::add(b2, O::mul(v[1][1], a2));
+    b2 = O::add(b2, O::mul(v[2][1], a3));
+    b3 = O::add(b3, O::mul(v[1][2], a2));
+    b3 = O::add(b3, O::mul(v[2][2], a3));
+    a[r][0] = b1; a[r][1] = b2; a[r][2] = b3;
+  }
+  auto colnorm = [&](int c) {
+    float r = O::mul(a[0][c], a[0][c]);
+    r = O::add(r, O::mul(a[1][c], a[1][c]));
+    r = O::add(r, O::mul(a[2][c], a[2][c]));
+    return r;
+  };
+  float n1 = colnorm(0), n2 = colnorm(1), n3 = colnorm(2);
+  // sort columns by norm; each swap negates one column so V stays a rotation
+#define MPM_SVD_SWAP(CA, CB, CN, NA, NB)                 \
+  {                                                      \
+    const bool sw = (NA) < (NB);                         \
+    if (sw) {                                            \
+      _Pragma("unroll") for (int r = 0; r < 3; ++r) {    \
+        swapf(a[r][CA], a[r][CB]);                       \
+        swapf(v[r][CA], v[r][CB]);                       \
+      }                                                  \
+      swapf(NA, NB);                                     \
+    }                                                    \
+    const float f = sw ? -1.0f : 1.0f;                   \
+    _Pragma("unroll") for (int r = 0; r < 3; ++r) {      \
+      a[r][CN] = O::mul(a[r][CN], f);                    \
+      v[r][CN] = O::mul(v[r][CN], f);                    \
+    }                                                    \
+  }
+  MPM_SVD_SWAP(0, 1, 1, n1, n2)
+  MPM_SVD_SWAP(0, 2, 0, n1, n3)
+  MPM_SVD_SWAP(1, 2, 2, n2, n3)
+#undef MPM_SVD_SWAP
+  float u[3][3] = {{1.f, 0.f, 0.f}, {0.f, 1.f, 0.f}, {0.f, 0.f, 1.f}};
+  float c, s;
+  givens<O>(a[0][0], a[1][0], c, s);
+#pragma unroll
+  for (int j = 0; j < 3; ++j) rot<O>(c, s, a[0][j], a[1][j]);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) rot<O>(c, s, u[i][0], u[i][1]);
+  givens<O>(a[0][0], a[2][0], c, s);
+#pragma unroll
+  for (int j = 0; j < 3; ++j) rot<O>(c, s, a[0][j], a[2][j]);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) rot<O>(c, s, u[i][0], u[i][2]);
+  givens<O>(a[1][1], a[2][1], c, s);
+#pragma unroll
+  for (int j = 0; j < 3; ++j) rot<O>(c, s, a[1][j], a[2][j]);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) rot<O>(c, s, u[i][1], u[i][2]);
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int cc = 0; cc < 3; ++cc) {
+      U.m[r][cc] = u[r][cc];
+      V.m[r][cc] = v[r][cc];
+    }
+  S[0] = a[0][0];
+  S[1] = a[1][1];
+  S[2] = a[2][2];
+}
+
+// 3x3 determinant, cofactor expansion along the first row (reference src/linalg.cu:47-52).
+__device__ __forceinline__ float det3(const Mat3& M) {
+  const float sub1 = M.m[1][0] * M.m[2][1] - M.m[1][1] * M.m[2][0];
+  const float sub2 = M.m[1][0] * M.m[2][2] - M.m[1][2] * M.m[2][0];
+  const float sub3 = M.m[1][1] * M.m[2][2] - M.m[1][2] * M.m[2][1];
+  return M.m[0][0] * sub3 - M.m[0][1] * sub2 + M.m[0][2] * sub1;
+}
+
+__device__ __forceinline__ Mat3 mul_abt(const Mat3& A, const Mat3& B) {  // A * B^T
+  Mat3 R;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) R.m[i][j] = A.m[i][0] * B.m[j][0] + A.m[i][1] * B.m[j][1] + A.m[i][2] * B.m[j][2];
+  return R;
+}
+__device__ __forceinline__ Mat3 mul_ab(const Mat3& A, const Mat3& B) {
+  Mat3 R;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) R.m[i][j] = A.m[i][0] * B.m[0][j] + A.m[i][1] * B.m[1][j] + A.m[i][2] * B.m[2][j];
+  return R;
+}
+
+// Rotation factor of the polar decomposition A = R S (reference src/linalg.cu:18-33: R = U V^T).
+template <class O>
+__device__ __forceinline__ Mat3 polar_rotation(const Mat3& A) {
+  Mat3 U, V;
+  float S[3];
+  svd3<O>(A, U, S, V);
+  return mul_abt(U, V);
+}
+
+}  // namespace mpm

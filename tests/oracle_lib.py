@@ -251,7 +251,7 @@ def dense_block_positions(count, seed=1234, lo=0.1, hi=0.9, first_id=0):
             h = lowbias32(((ids * np.uint64(3) + np.uint64(axis)) & np.uint64(0xFFFFFFFF)).astype(np.uint32)
                           ^ lowbias32(np.uint32(seed)))
         u = (h >> np.uint32(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)
-        out[:, axis] = np.float32(lo) + np.float32(hi - lo) * u
+        out[:, axis] = np.float32(lo) + (np.float32(hi) - np.float32(lo)) * u
     return out
 
 

@@ -1,0 +1,38 @@
+"""Small deterministic scenes shared by the CPU and GPU parity tests."""
+import numpy as np
+
+import oracle_lib as ol
+
+
+def two_spheres(N=32, density=500000.0, seed=1, kind=ol.SNOW, perturb=True):
+    """A resting ball and a smaller ball thrown at it (snowman-like, sphere.obj stand-in)."""
+    rng = np.random.default_rng(seed)
+    xa = ol.sphere_positions(density, 0.4, [0.3, 0.12, 0.3], rng)
+    xb = ol.sphere_positions(density, 0.2, [0.4, 0.6, 0.4], rng)
+    p = ol.new_particles(np.concatenate([xa, xb]))
+    p["v"][len(xa):] = [0.5, -3.0, 0.2]
+    if perturb:  # exercise F, C, Jp paths from step one
+        p["F"] += 0.02 * rng.standard_normal(p["F"].shape).astype(np.float32)
+        p["C"] = 5.0 * rng.standard_normal(p["C"].shape).astype(np.float32)
+        p["Jp"] = 1.0 + 0.05 * rng.standard_normal(len(p)).astype(np.float32)
+    if kind == ol.SNOW:
+        mats = ol.make_material(1.0 / density)  # scenes/snowman.toml
+    else:
+        mats = ol.make_material(1.0 / density, 1000.0, 1.4e5, 0.2, 0.0, 0.0, 1e30)
+        p["Jp"] = 1.0
+    return p, mats
+
+
+def dense_block(count, N, density=None, seed=1234):
+    """SURVEY.md 8(d) config 4 at reduced size: uniform block in [0.1,0.9]^3, fixed-corotated."""
+    x = ol.dense_block_positions(count, seed)
+    p = ol.new_particles(x)
+    dens = density if density is not None else count / 0.512
+    mats = ol.make_material(1.0 / dens, 1000.0, 1.4e5, 0.2, 0.0, 0.0, 1e30)
+    return p, mats
+
+
+def rel_err(a, b, floor):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return np.abs(a - b) / np.maximum(np.abs(b), floor)
