@@ -42,11 +42,12 @@ def peaks():
 
 def workload(gpus):
     """Cubic N and balanced slabs for `gpus` ranks, 2^26 particles each."""
+    from mpm_b200 import slabs
+
     if gpus == 1:
         return 256, [(0, 256)]
     N = int(round(256 * gpus ** (1.0 / 3.0) / 2) * 2)
-    cuts = [0] + [int(round(N * (0.1 + 0.8 * r / gpus))) for r in range(1, gpus)] + [N]
-    return N, [(cuts[r], cuts[r + 1]) for r in range(gpus)]
+    return N, slabs.balanced_slabs(N, gpus, 0.1, 0.9)
 
 
 class ClockSampler:
@@ -197,9 +198,9 @@ def main():
     sim = mpm_b200.Sim(N, dt, mats, model=mpm_b200.FIXED_COROTATED, svd_mode=svd_mode, sort_every=args.sort_every,
                        x_begin=xb, x_end=xe, device=local_rank, capacity=cap)
     if world > 1:
-        uid = [mpm_b200.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        sim.attach_comm(uid[0], rank, world)
+        from mpm_b200 import slabs as _slabs
+
+        sim.attach_comm(_slabs.share_unique_id(dist, rank, mpm_b200.comm_unique_id), rank, world)
     sim.generate_dense_block(P_total, seed=1234)
     sim.sync()
     P_local = sim.count

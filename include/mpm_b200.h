@@ -31,6 +31,9 @@ enum { MPM_MODEL_SNOW = 0, MPM_MODEL_FIXED_COROTATED = 1 };
 /* svd3 arithmetic: EXACT reproduces the reference svd3 bit for bit; FAST contracts to FMA and
  * uses the hardware rsqrt approximation (deviation reported by the tests) */
 enum { MPM_SVD_EXACT = 0, MPM_SVD_FAST = 1 };
+/* P2G kernel: RUNS pre-reduces same-cell particles in registers before the vector reductions
+ * (default); DIRECT issues 27 vector reductions per particle (also used when N > 1019) */
+enum { MPM_P2G_RUNS = 0, MPM_P2G_DIRECT = 1 };
 /* stage indices for mpm_get_stage_times */
 enum { MPM_STAGE_SORT = 0, MPM_STAGE_RESET = 1, MPM_STAGE_P2G = 2, MPM_STAGE_GRID = 3, MPM_STAGE_G2P = 4,
        MPM_STAGE_EXCHANGE = 5, MPM_STAGE_COUNT = 6 };
@@ -68,6 +71,9 @@ typedef struct MpmParams {
   uint32_t x_end;       /* one past the last owned x-plane (N for a single device; 0 means N) */
   int32_t device;       /* CUDA device ordinal, -1 = current */
   uint64_t capacity;    /* particle slots to allocate (0 = size of the first upload) */
+  uint32_t p2g_mode;    /* MPM_P2G_* */
+  uint32_t ghost;       /* slab handles: extra ghost x-planes either side, i.e. how many cells a particle
+                           may drift out of its slab between re-bins (0 = default: 1 for slabs) */
 } MpmParams;
 
 typedef struct MpmSim MpmSim;
@@ -86,6 +92,9 @@ int mpm_abi_version(void);
 
 /* particlesToDevice (src/mpm.cu:278-286): host AoS -> device SoA; replaces the active set */
 int mpm_upload_particles_aos(MpmSim* sim, const MpmParticle* particles, size_t count);
+/* slab handles (multi-GPU): same, with caller-chosen global particle ids; such handles return
+ * particles in their current (cell-sorted) order, ids via mpm_debug_download_sort */
+int mpm_upload_particles_with_ids(MpmSim* sim, const MpmParticle* particles, const uint32_t* ids, size_t count);
 /* particlesToHost (src/mpm.cu:288-306): blocking; particles come back in upload order */
 int mpm_download_particles_aos(MpmSim* sim, MpmParticle* particles, size_t capacity, size_t* count);
 /* positions only (12 B/particle), upload order — what the reference's viewer cadence needs */

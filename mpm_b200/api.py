@@ -8,6 +8,7 @@ from . import build as _build
 
 SNOW, FIXED_COROTATED = 0, 1
 SVD_EXACT, SVD_FAST = 0, 1
+P2G_RUNS, P2G_DIRECT = 0, 1
 STAGES = ("sort", "reset", "p2g", "grid", "g2p", "exchange")
 
 # MpmParticle == the reference's MLS_APIC_Particle (104 bytes, matrices column-major)
@@ -22,7 +23,8 @@ MATERIAL_DTYPE = np.dtype([(n, "f4") for n in ("particleVolume", "particleMass",
 class MpmParams(ctypes.Structure):
     _fields_ = [("dt", ctypes.c_float), ("N", ctypes.c_uint32), ("model", ctypes.c_uint32),
                 ("svd_mode", ctypes.c_uint32), ("sort_every", ctypes.c_uint32), ("x_begin", ctypes.c_uint32),
-                ("x_end", ctypes.c_uint32), ("device", ctypes.c_int32), ("capacity", ctypes.c_uint64)]
+                ("x_end", ctypes.c_uint32), ("device", ctypes.c_int32), ("capacity", ctypes.c_uint64),
+                ("p2g_mode", ctypes.c_uint32), ("ghost", ctypes.c_uint32)]
 
 
 class MpmError(RuntimeError):
@@ -38,7 +40,7 @@ def lib():
     """Loads (building if needed) libmpm_b200.so.  Raises if it cannot be had — no fallback."""
     global _lib
     if _lib is None:
-        path = _build.build()
+        path = os.environ.get("MPM_B200_LIB") or _build.build()  # MPM_B200_LIB: experiment builds (tools/ab.py)
         L = ctypes.CDLL(path)
         L.mpm_last_error.restype = ctypes.c_char_p
         L.mpm_last_error.argtypes = [_vp]
@@ -60,6 +62,7 @@ def lib():
         L.mpm_make_material.argtypes = [ctypes.c_double] * 7 + [_vp]
         L.mpm_create.argtypes = [ctypes.POINTER(MpmParams), _vp, ctypes.c_int, ctypes.POINTER(_vp)]
         L.mpm_upload_particles_aos.argtypes = [_vp, _vp, ctypes.c_size_t]
+        L.mpm_upload_particles_with_ids.argtypes = [_vp, _vp, _vp, ctypes.c_size_t]
         L.mpm_download_particles_aos.argtypes = [_vp, _vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
         L.mpm_download_positions.argtypes = [_vp, _vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
         L.mpm_generate_dense_block.argtypes = [_vp, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_float,
@@ -97,10 +100,10 @@ class Sim:
     """One handle = one device.  Mirrors the device half of the reference's Simulation class."""
 
     def __init__(self, N, dt, materials, model=SNOW, svd_mode=SVD_EXACT, sort_every=0, x_begin=0, x_end=0,
-                 device=-1, capacity=0):
+                 device=-1, capacity=0, p2g_mode=P2G_RUNS, ghost=0):
         self._h = _vp()
         mats = np.ascontiguousarray(materials, np.float32).reshape(-1, 7)
-        self.params = MpmParams(dt, N, model, svd_mode, sort_every, x_begin, x_end, device, capacity)
+        self.params = MpmParams(dt, N, model, svd_mode, sort_every, x_begin, x_end, device, capacity, p2g_mode, ghost)
         rc = lib().mpm_create(ctypes.byref(self.params), _ptr(mats), mats.shape[0], ctypes.byref(self._h))
         if rc:
             raise MpmError(lib().mpm_last_error(None).decode())
@@ -126,6 +129,11 @@ class Sim:
     def upload(self, particles):
         assert particles.dtype == PARTICLE_DTYPE and particles.flags.c_contiguous
         self._ck(lib().mpm_upload_particles_aos(self._h, _ptr(particles), particles.shape[0]))
+
+    def upload_with_ids(self, particles, ids):
+        assert particles.dtype == PARTICLE_DTYPE and particles.flags.c_contiguous
+        ids = np.ascontiguousarray(ids, np.uint32)
+        self._ck(lib().mpm_upload_particles_with_ids(self._h, _ptr(particles), _ptr(ids), particles.shape[0]))
 
     def upload_ptr(self, ptr, count):
         self._ck(lib().mpm_upload_particles_aos(self._h, _vp(ptr), count))

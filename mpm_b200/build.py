@@ -17,13 +17,25 @@ def _newest_source():
     return t
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, defines=(), out=None):
+    """defines/out: experiment builds (tools/ab.py), e.g. defines=("MPM_G2P_VARIANT=0",)."""
+    global LIB
+    lib_default = LIB
+    if out:
+        LIB = out
+    try:
+        return _build(force, verbose, defines)
+    finally:
+        LIB = lib_default
+
+
+def _build(force, verbose, defines):
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _newest_source():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-shared",
            "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++", "-Xptxas", "-v" if verbose else "-warn-spills",
-           "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lnccl"]
+           "-o", LIB] + ["-D" + d for d in defines] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lnccl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode:
         sys.stderr.write(r.stdout + r.stderr)

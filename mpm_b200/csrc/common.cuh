@@ -34,6 +34,8 @@ struct KParams {
   int x_own_begin, x_own_end;
 };
 
+constexpr uint32_t kDeadId = 0xffffffffu;  // tombstone of a particle that migrated to another rank
+
 __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fmaxf(fminf(x, hi), lo); }
 
 // quadratic B-spline weights and base node (reference include/InterpolationKernel.cuh:57-69);
@@ -67,7 +69,8 @@ __device__ __forceinline__ MpmMaterial load_material(const MpmMaterial* __restri
 // in double like the reference; FAST stays in f32 and skips exp when hardening == 0.
 template <int MODEL, class O, bool EXACT>
 __device__ __forceinline__ Mat3 compute_PF(const Mat3& F, float Jp, const MpmMaterial& m) {
-  const Mat3 R = polar_rotation<O>(F);
+  Mat3 R;
+  if constexpr (EXACT) R = polar_rotation<O>(F); else R = polar_rotation_newton(F);
   float mu = m.mu0, lambda = m.lambda0;
   if (MODEL == MPM_MODEL_SNOW) {
     float e;

@@ -30,7 +30,7 @@ __global__ void aos_to_soa_kernel(const MpmParticle* __restrict__ aos, Soa p, si
 }
 
 // writes particle r to aos[id[r] - first_id]: restores upload order
-__global__ void soa_to_aos_kernel(Soa p, size_t count, MpmParticle* __restrict__ aos, uint32_t first_id) {
+__global__ void soa_to_aos_kernel(Soa p, size_t count, MpmParticle* __restrict__ aos, uint32_t first_id, bool by_id) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
   MpmParticle q;
@@ -49,13 +49,13 @@ __global__ void soa_to_aos_kernel(Soa p, size_t count, MpmParticle* __restrict__
       q.C[3 * c + r] = p.s(SC + 3 * r + c)[i];
     }
   q.Jp = p.s(SJ)[i];
-  aos[p.id[i] - first_id] = q;
+  aos[by_id ? (size_t)(p.id[i] - first_id) : i] = q;  // slab handles: current (cell-sorted) order
 }
 
-__global__ void positions_kernel(Soa p, size_t count, float* __restrict__ xyz, uint32_t first_id) {
+__global__ void positions_kernel(Soa p, size_t count, float* __restrict__ xyz, uint32_t first_id, bool by_id) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
-  const size_t o = (size_t)(p.id[i] - first_id) * 3;
+  const size_t o = (by_id ? (size_t)(p.id[i] - first_id) : i) * 3;
   xyz[o + 0] = p.s(SX + 0)[i];
   xyz[o + 1] = p.s(SX + 1)[i];
   xyz[o + 2] = p.s(SX + 2)[i];
@@ -240,14 +240,41 @@ __global__ void __launch_bounds__(256) grid_update_kernel(float4* __restrict__ g
 // ---- stage (4): G2P ---------------------------------------------------------------------------
 // One thread per particle: 27 float4 node reads (sorted order -> L1/L2 hits), APIC C, F update,
 // plasticity, advection (reference src/mpm.cu:109-178, TransferScheme.h:102-142).
+// Tuning switches (tools/ab.py measures them on the same box; defaults = the fastest measured):
+#ifndef MPM_G2P_VARIANT
+#define MPM_G2P_VARIANT 0   // 0: per-node accumulation, 1: separable along z
+#endif
+#ifndef MPM_G2P_PREFETCH
+#define MPM_G2P_PREFETCH 0  // 1: issue the F loads before the gather
+#endif
+#ifndef MPM_G2P_MINBLK
+#define MPM_G2P_MINBLK 0    // __launch_bounds__ min blocks per SM (0 = unconstrained)
+#endif
+#ifndef MPM_G2P_BLOCK
+#define MPM_G2P_BLOCK 128
+#endif
+constexpr int kG2pBlock = MPM_G2P_BLOCK;
+
 template <int MODEL, class O>
-__global__ void __launch_bounds__(kParticleBlock)
+__global__ void
+#if MPM_G2P_MINBLK > 0
+__launch_bounds__(kG2pBlock, MPM_G2P_MINBLK)
+#else
+__launch_bounds__(kG2pBlock)
+#endif
 g2p_kernel(Soa p, size_t count, const MpmMaterial* __restrict__ mats, const float4* __restrict__ grid, KParams k) {
   const size_t pi = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (pi >= count) return;
   float x[3];
 #pragma unroll
   for (int a = 0; a < 3; ++a) x[a] = p.s(SX + a)[pi];
+  Mat3 F;
+#if MPM_G2P_PREFETCH
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) F.m[r][c] = p.s(SF + 3 * r + c)[pi];
+#endif
   int base[3];
   float fx[3], w[3][3];
 #pragma unroll
@@ -279,6 +306,7 @@ g2p_kernel(Soa p, size_t count, const MpmMaterial* __restrict__ mats, const floa
   for (int r = 0; r < 3; ++r)
 #pragma unroll
     for (int c = 0; c < 3; ++c) B.m[r][c] = 0.f;
+#if MPM_G2P_VARIANT == 0
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
 #pragma unroll
@@ -301,6 +329,44 @@ g2p_kernel(Soa p, size_t count, const MpmMaterial* __restrict__ mats, const floa
       }
     }
   }
+#else
+  // Separable accumulation: for each (i,j) row, s0 = sum_k wz_k v_k and s1 = sum_k wz_k dz_k v_k
+  // (the three k-nodes are one contiguous 48 B run), then one rank-1 update per row.  Nodes
+  // outside the domain / slab load as zero instead of branching.
+  float wzd[3], wxd[3], wyd[3];
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    wxd[q] = w[0][q] * d[0][q];
+    wyd[q] = w[1][q] * d[1][q];
+    wzd[q] = w[2][q] * d[2][q];
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const float4* row = gbase + ((long long)i * NN + (long long)j * k.N);
+      const bool okr = ok[0][i] && ok[1][j];
+      float s0[3] = {0.f, 0.f, 0.f}, s1[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+      for (int kz = 0; kz < 3; ++kz) {
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (okr && ok[2][kz]) g = __ldg(row + kz);
+        s0[0] += w[2][kz] * g.x; s0[1] += w[2][kz] * g.y; s0[2] += w[2][kz] * g.z;
+        s1[0] += wzd[kz] * g.x;  s1[1] += wzd[kz] * g.y;  s1[2] += wzd[kz] * g.z;
+      }
+      const float wij = w[0][i] * w[1][j];
+      const float wdx = wxd[i] * w[1][j];
+      const float wdy = w[0][i] * wyd[j];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        v[c] += wij * s0[c];
+        B.m[c][0] += wdx * s0[c];
+        B.m[c][1] += wdy * s0[c];
+        B.m[c][2] += wij * s1[c];
+      }
+    }
+  }
+#endif
   Mat3 C, G;
 #pragma unroll
   for (int r = 0; r < 3; ++r)
@@ -309,11 +375,12 @@ g2p_kernel(Soa p, size_t count, const MpmMaterial* __restrict__ mats, const floa
       C.m[r][c] = B.m[r][c] * k.dinv;
       G.m[r][c] = ((r == c) ? 1.0f : 0.0f) + k.dt * C.m[r][c];
     }
-  Mat3 F;
+#if !MPM_G2P_PREFETCH
 #pragma unroll
   for (int r = 0; r < 3; ++r)
 #pragma unroll
     for (int c = 0; c < 3; ++c) F.m[r][c] = p.s(SF + 3 * r + c)[pi];
+#endif
   F = mul_ab(G, F);  // F <- (I + dt C) F
   if (MODEL == MPM_MODEL_SNOW) {
     float Jp = p.s(SJ)[pi];
@@ -356,7 +423,8 @@ __global__ void polar_batch_kernel(const float* __restrict__ A, float* R, size_t
   if (i >= n) return;
   Mat3 a;
   for (int e = 0; e < 9; ++e) a.m[e / 3][e % 3] = A[9 * i + e];
-  const Mat3 r = polar_rotation<O>(a);
+  Mat3 r;  // the same routine compute_PF uses for this mode
+  if constexpr (O::kExact) r = polar_rotation<O>(a); else r = polar_rotation_newton(a);
   for (int e = 0; e < 9; ++e) R[9 * i + e] = r.m[e / 3][e % 3];
 }
 __global__ void det_batch_kernel(const float* __restrict__ A, float* det, size_t n) {

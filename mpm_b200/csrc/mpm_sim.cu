@@ -13,6 +13,7 @@
 #include "../../include/mpm_b200.h"
 #include "comm.cuh"
 #include "kernels.cuh"
+#include "p2g_runs.cuh"
 #include "sort.cuh"
 
 using namespace mpm;
@@ -47,6 +48,8 @@ struct MpmSim {
   uint32_t* scan_sums = nullptr;
   size_t scan_sums_len = 0;
   int key_bits = 0;
+  int ghost = 0;
+  bool whole_domain = true;
   int sorted_cur = 0;  // which keys[] buffer holds the keys of the current order
 
   MpmParticle* aos_stage = nullptr;  // device AoS staging for upload/download
@@ -155,17 +158,24 @@ struct StageTimer {
 // ---- stages -------------------------------------------------------------------------------------
 int do_sort(MpmSim* sim) {
   StageTimer tm(sim, MPM_STAGE_SORT);
-  const size_t n = sim->count;
   sim->steps_since_sort = 0;
+  size_t n_dead = 0;
+  if (sim->comm.active()) {  // leavers out (tombstoned), arrivals appended, before the re-bin
+    if (sim->comm.migrate(sim->soa[sim->cur], &sim->count, sim->capacity, sim->k, sim->stream, &sim->launches, &n_dead))
+      return fail(sim, "particle migration failed: %s", sim->comm.error());
+  }
+  const size_t n = sim->count;
   if (n == 0) return 0;
   Soa& src = sim->soa[sim->cur];
-  cell_key_kernel<<<blocks_for(n, 256), 256, 0, sim->stream>>>(src, n, sim->k, sim->keys[0], sim->vals[0]);
+  const uint32_t dead_key = 1u << sim->key_bits;
+  const int sort_bits = sim->key_bits + (sim->comm.active() ? 1 : 0);
+  cell_key_kernel<<<blocks_for(n, 256), 256, 0, sim->stream>>>(src, n, sim->k, sim->keys[0], sim->vals[0], dead_key);
   sim->launches++;
   const int n_tiles = (int)((n + kSortTile - 1) / kSortTile);
   const size_t table_len = (size_t)n_tiles * kRadix;
   const unsigned scan_blocks = blocks_for(table_len, kScanTile);
   int in = 0;
-  for (int shift = 0; shift < sim->key_bits; shift += kRadixBits) {
+  for (int shift = 0; shift < sort_bits; shift += kRadixBits) {
     radix_hist_kernel<<<n_tiles, kSortThreads, 0, sim->stream>>>(sim->keys[in], n, shift, sim->table, n_tiles);
     scan_tile_sums_kernel<<<scan_blocks, kScanThreads, 0, sim->stream>>>(sim->table, table_len, sim->scan_sums);
     scan_sums_kernel<<<1, 1024, 0, sim->stream>>>(sim->scan_sums, scan_blocks);
@@ -180,6 +190,7 @@ int do_sort(MpmSim* sim) {
   permute_kernel<<<blocks_for(n, 256), 256, 0, sim->stream>>>(src, dst, sim->vals[in], n);
   sim->launches++;
   sim->cur ^= 1;
+  sim->count = n - n_dead;  // tombstones were sorted behind the live particles
   CK(cudaGetLastError());
   return 0;
 }
@@ -193,8 +204,16 @@ int do_reset(MpmSim* sim) {
 template <int MODEL>
 int launch_p2g(MpmSim* sim) {
   const size_t n = sim->count;
-  const unsigned nb = blocks_for(n, kParticleBlock);
   Soa& p = sim->soa[sim->cur];
+  if (sim->par.p2g_mode == MPM_P2G_RUNS && sim->k.N + kKeyBias <= 1023) {
+    const unsigned nbr = blocks_for(n, kP2gBlock);
+    if (sim->par.svd_mode == MPM_SVD_EXACT)
+      p2g_runs_kernel<MODEL, ExactOps, true><<<nbr, kP2gBlock, 0, sim->stream>>>(p, n, sim->mats, sim->grid, sim->k);
+    else
+      p2g_runs_kernel<MODEL, FastOps, false><<<nbr, kP2gBlock, 0, sim->stream>>>(p, n, sim->mats, sim->grid, sim->k);
+    return 0;
+  }
+  const unsigned nb = blocks_for(n, kParticleBlock);
   if (sim->par.svd_mode == MPM_SVD_EXACT)
     p2g_kernel<MODEL, ExactOps, true><<<nb, kParticleBlock, 0, sim->stream>>>(p, n, sim->mats, sim->grid, sim->k);
   else
@@ -222,12 +241,12 @@ int do_grid(MpmSim* sim) {
 template <int MODEL>
 int launch_g2p(MpmSim* sim) {
   const size_t n = sim->count;
-  const unsigned nb = blocks_for(n, kParticleBlock);
+  const unsigned nb = blocks_for(n, kG2pBlock);
   Soa& p = sim->soa[sim->cur];
   if (sim->par.svd_mode == MPM_SVD_EXACT)
-    g2p_kernel<MODEL, ExactOps><<<nb, kParticleBlock, 0, sim->stream>>>(p, n, sim->mats, sim->grid, sim->k);
+    g2p_kernel<MODEL, ExactOps><<<nb, kG2pBlock, 0, sim->stream>>>(p, n, sim->mats, sim->grid, sim->k);
   else
-    g2p_kernel<MODEL, FastOps><<<nb, kParticleBlock, 0, sim->stream>>>(p, n, sim->mats, sim->grid, sim->k);
+    g2p_kernel<MODEL, FastOps><<<nb, kG2pBlock, 0, sim->stream>>>(p, n, sim->mats, sim->grid, sim->k);
   return 0;
 }
 int do_g2p(MpmSim* sim) {
@@ -270,8 +289,8 @@ int mpm_create(const MpmParams* params, const MpmMaterial* materials, int n_mate
   if (!params || !out) return fail(nullptr, "mpm_create: null argument");
   if (params->N < 4) return fail(nullptr, "mpm_create: N must be >= 4");
   if (n_materials < 1 || n_materials > 256 || !materials) return fail(nullptr, "mpm_create: need 1..256 materials");
-  if (params->model > MPM_MODEL_FIXED_COROTATED || params->svd_mode > MPM_SVD_FAST)
-    return fail(nullptr, "mpm_create: bad model / svd_mode");
+  if (params->model > MPM_MODEL_FIXED_COROTATED || params->svd_mode > MPM_SVD_FAST || params->p2g_mode > MPM_P2G_DIRECT)
+    return fail(nullptr, "mpm_create: bad model / svd_mode / p2g_mode");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -317,8 +336,10 @@ int mpm_create(const MpmParams* params, const MpmMaterial* materials, int n_mate
   k.dinv = (4.0f * k.dx_inv) * k.dx_inv;
   k.x_own_begin = xb;
   k.x_own_end = xe;
-  k.x0 = xb;
-  k.nxl = std::min(N, xe + 2) - xb;  // owned planes + up to 2 ghost planes above
+  sim->whole_domain = (xb == 0 && xe == N);
+  sim->ghost = sim->whole_domain ? 0 : (params->ghost ? (int)params->ghost : 1);
+  k.x0 = std::max(0, xb - sim->ghost);
+  k.nxl = std::min(N, xe + 2 + sim->ghost) - k.x0;  // owned + 2 stencil planes above + ghost planes either side
   sim->grid_nodes = (size_t)k.nxl * N * N;
   sim->key_bits = bits_for(sim->grid_nodes);
   CKC(cudaStreamCreateWithFlags(&sim->stream, cudaStreamNonBlocking));
@@ -366,7 +387,7 @@ void mpm_destroy(MpmSim* sim) {
 
 const char* mpm_last_error(const MpmSim* sim) { return sim ? sim->err.c_str() : g_create_error.c_str(); }
 
-int mpm_upload_particles_aos(MpmSim* sim, const MpmParticle* particles, size_t count) {
+static int upload_impl(MpmSim* sim, const MpmParticle* particles, size_t count, const uint32_t* ids) {
   if (!sim || (!particles && count)) return fail(sim, "mpm_upload_particles_aos: null argument");
   CK(cudaSetDevice(sim->device));
   if (int rc = ensure_capacity(sim, std::max<size_t>(count, 1))) return rc;
@@ -379,9 +400,18 @@ int mpm_upload_particles_aos(MpmSim* sim, const MpmParticle* particles, size_t c
     aos_to_soa_kernel<<<blocks_for(count, 256), 256, 0, sim->stream>>>(sim->aos_stage, sim->soa[0], count, 0);
     sim->launches++;
     CK(cudaGetLastError());
+    if (ids) CK(cudaMemcpyAsync(sim->soa[0].id, ids, sizeof(uint32_t) * count, cudaMemcpyHostToDevice, sim->stream));
   }
   // bin immediately: the substep kernels assume cell-sorted order for locality
   return do_sort(sim);
+}
+
+int mpm_upload_particles_aos(MpmSim* sim, const MpmParticle* particles, size_t count) {
+  return upload_impl(sim, particles, count, nullptr);
+}
+int mpm_upload_particles_with_ids(MpmSim* sim, const MpmParticle* particles, const uint32_t* ids, size_t count) {
+  if (sim && sim->whole_domain && ids) return fail(sim, "mpm_upload_particles_with_ids: only for slab handles");
+  return upload_impl(sim, particles, count, ids);
 }
 
 int mpm_download_particles_aos(MpmSim* sim, MpmParticle* particles, size_t capacity, size_t* count) {
@@ -391,7 +421,7 @@ int mpm_download_particles_aos(MpmSim* sim, MpmParticle* particles, size_t capac
   if (capacity < sim->count) return fail(sim, "mpm_download_particles_aos: capacity %zu < %zu", capacity, sim->count);
   if (sim->count == 0) return 0;
   if (int rc = ensure_stage(sim, sim->count)) return rc;
-  soa_to_aos_kernel<<<blocks_for(sim->count, 256), 256, 0, sim->stream>>>(sim->soa[sim->cur], sim->count, sim->aos_stage, sim->first_id);
+  soa_to_aos_kernel<<<blocks_for(sim->count, 256), 256, 0, sim->stream>>>(sim->soa[sim->cur], sim->count, sim->aos_stage, sim->first_id, sim->whole_domain);
   sim->launches++;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(particles, sim->aos_stage, sizeof(MpmParticle) * sim->count, cudaMemcpyDeviceToHost, sim->stream));
@@ -407,7 +437,7 @@ int mpm_download_positions(MpmSim* sim, float* xyz, size_t capacity, size_t* cou
   if (sim->count == 0) return 0;
   if (int rc = ensure_stage(sim, (sim->count * 12 + sizeof(MpmParticle) - 1) / sizeof(MpmParticle))) return rc;
   float* stage = reinterpret_cast<float*>(sim->aos_stage);
-  positions_kernel<<<blocks_for(sim->count, 256), 256, 0, sim->stream>>>(sim->soa[sim->cur], sim->count, stage, sim->first_id);
+  positions_kernel<<<blocks_for(sim->count, 256), 256, 0, sim->stream>>>(sim->soa[sim->cur], sim->count, stage, sim->first_id, sim->whole_domain);
   sim->launches++;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(xyz, stage, sizeof(float) * 3 * sim->count, cudaMemcpyDeviceToHost, sim->stream));
@@ -418,7 +448,7 @@ int mpm_download_positions(MpmSim* sim, float* xyz, size_t capacity, size_t* cou
 int mpm_generate_dense_block(MpmSim* sim, uint64_t first_id, uint64_t count, uint32_t seed, float lo, float hi, uint8_t material) {
   if (!sim) return 1;
   CK(cudaSetDevice(sim->device));
-  const bool whole = (sim->k.x_own_begin == 0 && sim->k.x_own_end == sim->k.N);
+  const bool whole = sim->whole_domain;
   if (whole) {
     if (int rc = ensure_capacity(sim, std::max<uint64_t>(count, 1))) return rc;
   } else if (sim->capacity == 0) {
@@ -528,7 +558,8 @@ int mpm_comm_unique_id(void* id128) { return Comm::unique_id(id128); }
 int mpm_attach_comm(MpmSim* sim, const void* id128, int rank, int nranks) {
   if (!sim) return 1;
   CK(cudaSetDevice(sim->device));
-  if (int rc = sim->comm.init(id128, rank, nranks, sim->k, sim->stream)) return fail(sim, "mpm_attach_comm: %s", sim->comm.error());
+  if (sim->capacity == 0) return fail(sim, "mpm_attach_comm: set MpmParams.capacity for slab handles");
+  if (sim->comm.init(id128, rank, nranks, sim->k, sim->ghost, sim->capacity, sim->stream)) return fail(sim, "mpm_attach_comm: %s", sim->comm.error());
   return 0;
 }
 

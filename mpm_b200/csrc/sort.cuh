@@ -19,9 +19,16 @@ constexpr int kRadixBits = 8;
 constexpr int kRadix = 1 << kRadixBits;
 
 // key = N^2*bi + N*bj + bk of the clamped base node, bi local to the slab
-__global__ void cell_key_kernel(Soa p, size_t count, KParams k, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+// tombstoned particles (migrated away) get dead_key, which sorts behind every live key
+__global__ void cell_key_kernel(Soa p, size_t count, KParams k, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                                uint32_t dead_key) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
+  vals[i] = (uint32_t)i;
+  if (p.id[i] == kDeadId) {
+    keys[i] = dead_key;
+    return;
+  }
   int b[3];
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
@@ -31,7 +38,6 @@ __global__ void cell_key_kernel(Soa p, size_t count, KParams k, uint32_t* __rest
   }
   const int bx = min(max(b[0] - k.x0, 0), k.nxl - 1);
   keys[i] = (uint32_t)((bx * k.N + b[1]) * k.N + b[2]);
-  vals[i] = (uint32_t)i;
 }
 
 // (a) table[d * n_tiles + tile] = number of keys of this tile whose digit is d

@@ -16,12 +16,14 @@
 namespace mpm {
 
 struct ExactOps {
+  static constexpr bool kExact = true;
   static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
   static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
   static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
   static __device__ __forceinline__ float rsqrt(float x) { return __frsqrt_rn(x); }
 };
 struct FastOps {
+  static constexpr bool kExact = false;
   static __device__ __forceinline__ float mul(float a, float b) { return a * b; }
   static __device__ __forceinline__ float add(float a, float b) { return a + b; }
   static __device__ __forceinline__ float sub(float a, float b) { return a - b; }
@@ -343,6 +345,50 @@ __device__ __forceinline__ Mat3 polar_rotation(const Mat3& A) {
   float S[3];
   svd3<O>(A, U, S, V);
   return mul_abt(U, V);
+}
+
+// FAST-mode polar rotation: Newton iteration X <- (X + X^-T)/2 (Higham), quadratically convergent
+// and ~45 instructions per step against ~1300 for a full svd3.  It converges to the orthogonal
+// polar factor, which equals the reference's R = U V^T exactly when det(A) > 0; inverted or
+// near-singular elements (det <= 1e-6 * |A|^3, rare) take the svd3 route so the sign convention of
+// the reference (U, V proper rotations, sigma_3 < 0) is kept.  More accurate than svd3's R
+// (which carries the 4-sweep Jacobi error of ~1e-6); the deviation is reported by the tests.
+__device__ __forceinline__ Mat3 polar_rotation_newton(const Mat3& A) {
+  const float d = det3(A);
+  float n2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) n2 += A.m[i][j] * A.m[i][j];
+  if (!(d > 1e-6f * n2 * sqrtf(n2))) return polar_rotation<FastOps>(A);
+  Mat3 X = A;
+#pragma unroll 1
+  for (int it = 0; it < 16; ++it) {
+    // cofactor matrix = det * X^-T
+    Mat3 Cf;
+    Cf.m[0][0] = X.m[1][1] * X.m[2][2] - X.m[1][2] * X.m[2][1];
+    Cf.m[0][1] = X.m[1][2] * X.m[2][0] - X.m[1][0] * X.m[2][2];
+    Cf.m[0][2] = X.m[1][0] * X.m[2][1] - X.m[1][1] * X.m[2][0];
+    Cf.m[1][0] = X.m[0][2] * X.m[2][1] - X.m[0][1] * X.m[2][2];
+    Cf.m[1][1] = X.m[0][0] * X.m[2][2] - X.m[0][2] * X.m[2][0];
+    Cf.m[1][2] = X.m[0][1] * X.m[2][0] - X.m[0][0] * X.m[2][1];
+    Cf.m[2][0] = X.m[0][1] * X.m[1][2] - X.m[0][2] * X.m[1][1];
+    Cf.m[2][1] = X.m[0][2] * X.m[1][0] - X.m[0][0] * X.m[1][2];
+    Cf.m[2][2] = X.m[0][0] * X.m[1][1] - X.m[0][1] * X.m[1][0];
+    const float det = X.m[0][0] * Cf.m[0][0] + X.m[0][1] * Cf.m[0][1] + X.m[0][2] * Cf.m[0][2];
+    const float h = 0.5f / det;
+    float delta = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const float xn = 0.5f * X.m[i][j] + h * Cf.m[i][j];
+        delta = fmaxf(delta, fabsf(xn - X.m[i][j]));
+        X.m[i][j] = xn;
+      }
+    if (delta < 5e-7f) break;  // quadratic convergence: the next step would be ~1e-13
+  }
+  return X;
 }
 
 }  // namespace mpm

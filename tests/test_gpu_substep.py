@@ -55,10 +55,11 @@ def test_dense_block_generator_matches_host():
 
 @pytest.mark.parametrize("kind", [ol.SNOW, ol.FIXED_COROTATED])
 @pytest.mark.parametrize("mode", MODES)
-def test_p2g_single_step(kind, mode):
+@pytest.mark.parametrize("p2g_mode", [0, 1])  # MPM_P2G_RUNS, MPM_P2G_DIRECT
+def test_p2g_single_step(kind, mode, p2g_mode):
     N = 32
     p, mats = scenes.two_spheres(N, kind=kind)
-    sim = _sim(N, mats, kind, mode)
+    sim = _sim(N, mats, kind, mode, p2g_mode=p2g_mode)
     sim.upload(p)
     sim.stage("reset_grid")
     sim.stage("p2g")
@@ -108,7 +109,10 @@ def test_g2p_single_step_from_identical_grid(kind, mode):
     tol = 1e-5 if mode == 0 else 5e-5
     assert scenes.rel_err(got["x"], ref["x"], 1e-2).max() < 1e-6
     assert scenes.rel_err(got["v"], ref["v"], 1e-2).max() < tol
-    assert scenes.rel_err(got["C"], ref["C"], 1.0).max() < tol
+    # C = 4/dx^2 * sum_i w v_i d_i^T: 27 terms of magnitude |v| * 4N/... that cancel; the summation
+    # order differs (separable accumulation), so the bound is relative to the term magnitude
+    c_scale = 4.0 * N * np.abs(go[..., :3]).max()
+    assert np.abs(got["C"].astype(np.float64) - ref["C"]).max() < 1e-6 * c_scale
     assert scenes.rel_err(got["F"], ref["F"], 1.0).max() < tol
     assert scenes.rel_err(got["Jp"], ref["Jp"], 1.0).max() < tol
 
