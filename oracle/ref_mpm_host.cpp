@@ -1,12 +1,12 @@
 // TEST INFRASTRUCTURE ONLY (oracle/).  Host build of the reference's OWN substep code:
 //   include/types.h, linalg.h, svd3_cuda.h, MaterialModel.cuh, InterpolationKernel.cuh,
 //   TransferScheme.h                      — included unmodified from $(REF)/include
-//   src/linalg.cu:18-53 (device half)     — extracted at build time into _ref/gen_linalg.inc
-//   src/mpm.cu:6-8,14-178 (three kernels) — extracted at build time into _ref/gen_kernels.inc
+//   src/linalg.cu:18-53 (device half)     — extracted at build time into a temp dir (gen_linalg.inc)
+//   src/mpm.cu:6-8,14-178 (three kernels) — extracted at build time into a temp dir (gen_kernels.inc)
 // compiled against the Eigen shim in oracle/shim (Eigen itself is not in this image), with the
 // CUDA execution model replaced by a serial loop: one call of the kernel function per
 // (blockIdx, threadIdx).  Nothing from the reference is copied into the repository; the .inc
-// files live in the git-ignored oracle/_ref/.  Result: oracle/_ref/libref_mpm_{snow,fc}.so, the
+// files live in a temporary directory during the build only.  Result: oracle/_ref/libref_mpm_{snow,fc}.so, the
 // "reference itself run here" that pins oracle/mpm_oracle.cpp (tests/test_oracle.py).
 // Caveats (documented in DESIGN.md): host float arithmetic without FMA contraction, whereas the
 // reference's nvcc build contracts; the kernels are launched only for particle counts <= N^3
