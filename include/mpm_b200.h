@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define MPM_B200_ABI_VERSION 1
+#define MPM_B200_ABI_VERSION 2
 
 /* which MaterialModel alias the kernels are instantiated for (reference include/mpm.cuh:25) */
 enum { MPM_MODEL_SNOW = 0, MPM_MODEL_FIXED_COROTATED = 1 };
@@ -34,6 +34,9 @@ enum { MPM_SVD_EXACT = 0, MPM_SVD_FAST = 1 };
 /* P2G kernel: RUNS pre-reduces same-cell particles in registers before the vector reductions
  * (default); DIRECT issues 27 vector reductions per particle (also used when N > 1019) */
 enum { MPM_P2G_RUNS = 0, MPM_P2G_DIRECT = 1 };
+/* G2P kernel: TILE stages the grid block and the particle streams of each CTA in shared memory
+ * with bulk async copies (default); DIRECT gathers the 27 nodes per particle from global memory */
+enum { MPM_G2P_TILE = 0, MPM_G2P_DIRECT = 1 };
 /* stage indices for mpm_get_stage_times */
 enum { MPM_STAGE_SORT = 0, MPM_STAGE_RESET = 1, MPM_STAGE_P2G = 2, MPM_STAGE_GRID = 3, MPM_STAGE_G2P = 4,
        MPM_STAGE_EXCHANGE = 5, MPM_STAGE_COUNT = 6 };
@@ -74,6 +77,8 @@ typedef struct MpmParams {
   uint32_t p2g_mode;    /* MPM_P2G_* */
   uint32_t ghost;       /* slab handles: extra ghost x-planes either side, i.e. how many cells a particle
                            may drift out of its slab between re-bins (0 = default: 1 for slabs) */
+  uint32_t g2p_mode;    /* MPM_G2P_* */
+  uint32_t reserved_;   /* must be 0 */
 } MpmParams;
 
 typedef struct MpmSim MpmSim;
@@ -124,6 +129,9 @@ int mpm_stage_g2p(MpmSim* sim);         /* gridToParticle, src/mpm.cu:109-178 */
 /* debug access to internal state (parity tests) */
 int mpm_debug_download_grid(MpmSim* sim, float* vec4, size_t n_nodes);       /* local slab incl. ghost planes */
 int mpm_debug_upload_grid(MpmSim* sim, const float* vec4, size_t n_nodes);
+/* replaces the particle data in place (particles in upload order, same count) WITHOUT re-binning:
+ * tests use it to present the kernels with a stale cell order */
+int mpm_debug_overwrite_particles_aos(MpmSim* sim, const MpmParticle* particles, size_t count);
 int mpm_debug_download_sort(MpmSim* sim, uint32_t* keys, uint32_t* ids, size_t capacity); /* current order */
 size_t mpm_grid_nodes(const MpmSim* sim);
 

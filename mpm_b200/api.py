@@ -9,6 +9,7 @@ from . import build as _build
 SNOW, FIXED_COROTATED = 0, 1
 SVD_EXACT, SVD_FAST = 0, 1
 P2G_RUNS, P2G_DIRECT = 0, 1
+G2P_TILE, G2P_DIRECT = 0, 1
 STAGES = ("sort", "reset", "p2g", "grid", "g2p", "exchange")
 
 # MpmParticle == the reference's MLS_APIC_Particle (104 bytes, matrices column-major)
@@ -24,7 +25,8 @@ class MpmParams(ctypes.Structure):
     _fields_ = [("dt", ctypes.c_float), ("N", ctypes.c_uint32), ("model", ctypes.c_uint32),
                 ("svd_mode", ctypes.c_uint32), ("sort_every", ctypes.c_uint32), ("x_begin", ctypes.c_uint32),
                 ("x_end", ctypes.c_uint32), ("device", ctypes.c_int32), ("capacity", ctypes.c_uint64),
-                ("p2g_mode", ctypes.c_uint32), ("ghost", ctypes.c_uint32)]
+                ("p2g_mode", ctypes.c_uint32), ("ghost", ctypes.c_uint32), ("g2p_mode", ctypes.c_uint32),
+                ("reserved_", ctypes.c_uint32)]
 
 
 class MpmError(RuntimeError):
@@ -73,6 +75,7 @@ def lib():
             getattr(L, n).argtypes = [_vp]
         L.mpm_debug_download_grid.argtypes = [_vp, _vp, ctypes.c_size_t]
         L.mpm_debug_upload_grid.argtypes = [_vp, _vp, ctypes.c_size_t]
+        L.mpm_debug_overwrite_particles_aos.argtypes = [_vp, _vp, ctypes.c_size_t]
         L.mpm_debug_download_sort.argtypes = [_vp, _vp, _vp, ctypes.c_size_t]
         L.mpm_get_stage_times.argtypes = [_vp, _vp]
         L.mpm_comm_unique_id.argtypes = [_vp]
@@ -100,10 +103,10 @@ class Sim:
     """One handle = one device.  Mirrors the device half of the reference's Simulation class."""
 
     def __init__(self, N, dt, materials, model=SNOW, svd_mode=SVD_EXACT, sort_every=0, x_begin=0, x_end=0,
-                 device=-1, capacity=0, p2g_mode=P2G_RUNS, ghost=0):
+                 device=-1, capacity=0, p2g_mode=P2G_RUNS, ghost=0, g2p_mode=G2P_TILE):
         self._h = _vp()
         mats = np.ascontiguousarray(materials, np.float32).reshape(-1, 7)
-        self.params = MpmParams(dt, N, model, svd_mode, sort_every, x_begin, x_end, device, capacity, p2g_mode, ghost)
+        self.params = MpmParams(dt, N, model, svd_mode, sort_every, x_begin, x_end, device, capacity, p2g_mode, ghost, g2p_mode, 0)
         rc = lib().mpm_create(ctypes.byref(self.params), _ptr(mats), mats.shape[0], ctypes.byref(self._h))
         if rc:
             raise MpmError(lib().mpm_last_error(None).decode())
@@ -129,6 +132,11 @@ class Sim:
     def upload(self, particles):
         assert particles.dtype == PARTICLE_DTYPE and particles.flags.c_contiguous
         self._ck(lib().mpm_upload_particles_aos(self._h, _ptr(particles), particles.shape[0]))
+
+    def overwrite(self, particles):
+        """New particle data (upload order) into the existing slots, without re-binning."""
+        assert particles.dtype == PARTICLE_DTYPE and particles.flags.c_contiguous
+        self._ck(lib().mpm_debug_overwrite_particles_aos(self._h, _ptr(particles), particles.shape[0]))
 
     def upload_with_ids(self, particles, ids):
         assert particles.dtype == PARTICLE_DTYPE and particles.flags.c_contiguous

@@ -9,10 +9,12 @@
 namespace mpm {
 
 // ---- particle streams in HBM ------------------------------------------------------------------
-// 25 float streams (x3, v3, F9 row-major, C9 row-major, Jp), each `stride` floats long and
+// 25 float streams (x3, F9 row-major, Jp, v3, C9 row-major), each `stride` floats long and
 // 128-byte aligned, so a warp reading stream s for 32 consecutive particles touches exactly one
-// 128 B line.  Plus u32 id (upload order, for un-permuting on download) and u8 material.
-enum : int { SX = 0, SV = 3, SF = 6, SC = 15, SJ = 24, NSTREAM = 25 };
+// 128 B line.  Seen as a 2-D tensor [NSTREAM][stride], what G2P reads (x, F, Jp) is rows 0..12 and
+// what P2G reads is rows 0..24: one TMA box each.  Plus u32 id (upload order, for un-permuting on
+// download) and u8 material.
+enum : int { SX = 0, SF = 3, SJ = 12, SV = 13, SC = 16, NSTREAM = 25 };
 
 struct Soa {
   float* f;       // NSTREAM * stride floats

@@ -2,6 +2,7 @@
 // Reference behaviour: src/mpm.cu:14-178 + include/TransferScheme.h:66-142.
 #pragma once
 #include "common.cuh"
+#include "f32x2.cuh"
 
 namespace mpm {
 
@@ -26,6 +27,27 @@ __global__ void aos_to_soa_kernel(const MpmParticle* __restrict__ aos, Soa p, si
     }
   p.s(SJ)[i] = q.Jp;
   p.id[i] = first_id + (uint32_t)i;
+  p.mat[i] = q.material_type;
+}
+
+// slot r <- aos[id[r] - first_id]: new particle data into the existing (cell-sorted) slots
+__global__ void aos_overwrite_kernel(const MpmParticle* __restrict__ aos, Soa p, size_t count, uint32_t first_id) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const MpmParticle& q = aos[p.id[i] - first_id];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    p.s(SX + a)[i] = q.x[a];
+    p.s(SV + a)[i] = q.v[a];
+  }
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      p.s(SF + 3 * r + c)[i] = q.F[3 * c + r];
+      p.s(SC + 3 * r + c)[i] = q.C[3 * c + r];
+    }
+  p.s(SJ)[i] = q.Jp;
   p.mat[i] = q.material_type;
 }
 
@@ -238,135 +260,180 @@ __global__ void __launch_bounds__(256) grid_update_kernel(float4* __restrict__ g
 }
 
 // ---- stage (4): G2P ---------------------------------------------------------------------------
-// One thread per particle: 27 float4 node reads (sorted order -> L1/L2 hits), APIC C, F update,
-// plasticity, advection (reference src/mpm.cu:109-178, TransferScheme.h:102-142).
-// Tuning switches (tools/ab.py measures them on the same box; defaults = the fastest measured):
-#ifndef MPM_G2P_VARIANT
-#define MPM_G2P_VARIANT 0   // 0: per-node accumulation, 1: separable along z
-#endif
-#ifndef MPM_G2P_PREFETCH
-#define MPM_G2P_PREFETCH 0  // 1: issue the F loads before the gather
-#endif
+// One thread per particle (reference src/mpm.cu:109-178, TransferScheme.h:102-142).
+//
+// The kernel is issue-bound before it is HBM-bound, so the gather is written for few issue slots:
+//   * separable along z: per (i,j) row s0 = sum_k wz_k v_k and s1 = sum_k wz_k dz_k v_k (the three
+//     k-nodes are one contiguous 48 B run), then one rank-1 update of (v, B) per row;
+//   * the x,y components travel as packed pairs (FFMA2, f32x2.cuh), z as scalars;
+//   * warps whose 32 particles all have their whole stencil inside the local grid (every warp away
+//     from the domain faces) take a path with no per-node predicates; the others take the generic
+//     per-node path below, which clips like the reference.
 #ifndef MPM_G2P_MINBLK
-#define MPM_G2P_MINBLK 0    // __launch_bounds__ min blocks per SM (0 = unconstrained)
+#define MPM_G2P_MINBLK 8    // __launch_bounds__ min blocks per SM (64 regs: occupancy beats ILP here, tools/ab.py)
 #endif
 #ifndef MPM_G2P_BLOCK
 #define MPM_G2P_BLOCK 128
 #endif
+#ifndef MPM_G2P_STREAMING
+#define MPM_G2P_STREAMING 1  // particle streams are touched once per kernel: evict-first loads / streaming stores
+#endif
+#ifndef MPM_G2P_PREFETCH
+#define MPM_G2P_PREFETCH 0   // 1: issue the F loads together with the x loads
+#endif
+#if MPM_G2P_STREAMING
+#define MPM_LDP(ptr) __ldcs(ptr)
+#define MPM_STP(ptr, val) __stcs(ptr, val)
+#else
+#define MPM_LDP(ptr) (*(ptr))
+#define MPM_STP(ptr, val) (*(ptr) = (val))
+#endif
 constexpr int kG2pBlock = MPM_G2P_BLOCK;
 
+// generic gather with per-node clipping (domain faces, slab edges); B = sum_i w v_i d_i^T.
+// Deliberately not inlined and fed by value: the rare clipped warps pay a call, the interior path
+// keeps its registers.
+struct G2pGather {
+  float v[3];
+  float B[3][3];
+};
+__device__ __noinline__ G2pGather g2p_gather_clipped(const float4* __restrict__ grid, KParams k, float x0, float x1, float x2) {
+  const float x[3] = {x0, x1, x2};
+  int base[3];
+  float fx[3], w[3][3], d[3][3];
+  for (int a = 0; a < 3; ++a) {
+    bspline(x[a], k.dx_inv, base[a], fx[a], w[a]);
+    for (int i = 0; i < 3; ++i) d[a][i] = (float)(base[a] + i) * k.dx - x[a];
+  }
+  G2pGather o;
+  for (int c = 0; c < 3; ++c) {
+    o.v[c] = 0.f;
+    for (int a = 0; a < 3; ++a) o.B[c][a] = 0.f;
+  }
+  const long long NN = (long long)k.N * k.N;
+  const float4* gbase = grid + ((long long)(base[0] - k.x0) * NN + (long long)base[1] * k.N + base[2]);
+  for (int i = 0; i < 3; ++i) {
+    const int gx = base[0] + i;
+    if (gx < 0 || gx >= k.N || gx < k.x0 || gx >= k.x0 + k.nxl) continue;
+    for (int j = 0; j < 3; ++j) {
+      const int gy = base[1] + j;
+      if (gy < 0 || gy >= k.N) continue;
+      const float wij = w[0][i] * w[1][j];
+      for (int kz = 0; kz < 3; ++kz) {
+        const int gz = base[2] + kz;
+        if (gz < 0 || gz >= k.N) continue;
+        const float4 g = __ldg(gbase + ((long long)i * NN + j * k.N + kz));
+        const float wt = wij * w[2][kz];
+        const float wv[3] = {wt * g.x, wt * g.y, wt * g.z};
+        for (int c = 0; c < 3; ++c) {
+          o.v[c] += wv[c];
+          o.B[c][0] += wv[c] * d[0][i];
+          o.B[c][1] += wv[c] * d[1][j];
+          o.B[c][2] += wv[c] * d[2][kz];
+        }
+      }
+    }
+  }
+  return o;
+}
+
 template <int MODEL, class O>
-__global__ void
-#if MPM_G2P_MINBLK > 0
-__launch_bounds__(kG2pBlock, MPM_G2P_MINBLK)
-#else
-__launch_bounds__(kG2pBlock)
-#endif
+__global__ void __launch_bounds__(kG2pBlock, MPM_G2P_MINBLK)
 g2p_kernel(Soa p, size_t count, const MpmMaterial* __restrict__ mats, const float4* __restrict__ grid, KParams k) {
   const size_t pi = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (pi >= count) return;
-  float x[3];
+  const bool live = pi < count;
+  float x[3] = {0.f, 0.f, 0.f};
+  if (live) {
 #pragma unroll
-  for (int a = 0; a < 3; ++a) x[a] = p.s(SX + a)[pi];
+    for (int a = 0; a < 3; ++a) x[a] = MPM_LDP(p.s(SX + a) + pi);
+  }
   Mat3 F;
 #if MPM_G2P_PREFETCH
+  if (live) {
 #pragma unroll
-  for (int r = 0; r < 3; ++r)
+    for (int r = 0; r < 3; ++r)
 #pragma unroll
-    for (int c = 0; c < 3; ++c) F.m[r][c] = p.s(SF + 3 * r + c)[pi];
+      for (int c = 0; c < 3; ++c) F.m[r][c] = MPM_LDP(p.s(SF + 3 * r + c) + pi);
+  }
 #endif
   int base[3];
   float fx[3], w[3][3];
 #pragma unroll
   for (int a = 0; a < 3; ++a) bspline(x[a], k.dx_inv, base[a], fx[a], w[a]);
+  bool inside = live, interior = true;
 #pragma unroll
-  for (int a = 0; a < 3; ++a)
-    if (base[a] + 3 < 0 || base[a] >= k.N) return;  // untouched, like the reference's early return
+  for (int a = 0; a < 3; ++a) {
+    inside = inside && !(base[a] + 3 < 0 || base[a] >= k.N);  // else untouched, like the reference's early return
+    interior = interior && base[a] >= 0 && base[a] + 2 < k.N;
+  }
+  interior = interior && base[0] >= k.x0 && base[0] + 2 < k.x0 + k.nxl;
+  const bool fast = __all_sync(0xffffffffu, interior || !inside);
+  if (!inside) return;
 
-  bool ok[3][3];
+  float v[3];
+  Mat3 B;  // sum_i w v_i d_i^T, scaled by dinv at the end
+  if (fast) {
+    float d[3][3];  // node - particle distance per axis (world units)
 #pragma unroll
-  for (int a = 0; a < 3; ++a)
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int i = 0; i < 3; ++i) d[a][i] = (float)(base[a] + i) * k.dx - x[a];
+    const long long NN = (long long)k.N * k.N;
+    const float4* gbase = grid + ((long long)(base[0] - k.x0) * NN + (long long)base[1] * k.N + base[2]);
+    float wzd[3], wxd[3], wyd[3];
+    f2 WZ[3], WZD[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      wxd[q] = w[0][q] * d[0][q];
+      wyd[q] = w[1][q] * d[1][q];
+      wzd[q] = w[2][q] * d[2][q];
+      WZ[q] = dup2(w[2][q]);
+      WZD[q] = dup2(wzd[q]);
+    }
+    f2 Vxy = pack2(0.f, 0.f), B0xy = Vxy, B1xy = Vxy, B2xy = Vxy;  // B?xy = (B[0][?], B[1][?])
+    float vz = 0.f, B0z = 0.f, B1z = 0.f, B2z = 0.f;                // B?z  = B[2][?]
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-      const int g = base[a] + i;
-      ok[a][i] = (g >= 0) && (g < k.N);
-      if (a == 0) ok[a][i] = ok[a][i] && (g >= k.x0) && (g < k.x0 + k.nxl);
-    }
-  float d[3][3];  // node - particle distance per axis (world units)
 #pragma unroll
-  for (int a = 0; a < 3; ++a)
-#pragma unroll
-    for (int i = 0; i < 3; ++i) d[a][i] = (float)(base[a] + i) * k.dx - x[a];
-
-  const long long NN = (long long)k.N * k.N;
-  const float4* gbase = grid + ((long long)(base[0] - k.x0) * NN + (long long)base[1] * k.N + base[2]);
-  float v[3] = {0.f, 0.f, 0.f};
-  Mat3 B;  // sum_i w v_i d_i^T, scaled by dinv at the end
-#pragma unroll
-  for (int r = 0; r < 3; ++r)
-#pragma unroll
-    for (int c = 0; c < 3; ++c) B.m[r][c] = 0.f;
-#if MPM_G2P_VARIANT == 0
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      const float wij = w[0][i] * w[1][j];
-#pragma unroll
-      for (int kz = 0; kz < 3; ++kz) {
-        if (ok[0][i] && ok[1][j] && ok[2][kz]) {
-          const float4 g = __ldg(gbase + ((long long)i * NN + j * k.N + kz));
-          const float wt = wij * w[2][kz];
-          const float wv[3] = {wt * g.x, wt * g.y, wt * g.z};
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            v[c] += wv[c];
-            B.m[c][0] += wv[c] * d[0][i];
-            B.m[c][1] += wv[c] * d[1][j];
-            B.m[c][2] += wv[c] * d[2][kz];
-          }
-        }
+      for (int j = 0; j < 3; ++j) {
+        const float4* row = gbase + ((long long)i * NN + (long long)j * k.N);
+        const float4 g0 = __ldg(row), g1 = __ldg(row + 1), g2 = __ldg(row + 2);
+        f2 s0 = mul2(WZ[0], pack2(g0.x, g0.y));
+        f2 s1 = mul2(WZD[0], pack2(g0.x, g0.y));
+        float s0z = w[2][0] * g0.z, s1z = wzd[0] * g0.z;
+        s0 = fma2(WZ[1], pack2(g1.x, g1.y), s0);
+        s1 = fma2(WZD[1], pack2(g1.x, g1.y), s1);
+        s0z = fmaf(w[2][1], g1.z, s0z);
+        s1z = fmaf(wzd[1], g1.z, s1z);
+        s0 = fma2(WZ[2], pack2(g2.x, g2.y), s0);
+        s1 = fma2(WZD[2], pack2(g2.x, g2.y), s1);
+        s0z = fmaf(w[2][2], g2.z, s0z);
+        s1z = fmaf(wzd[2], g2.z, s1z);
+        const float wij = w[0][i] * w[1][j], wdx = wxd[i] * w[1][j], wdy = w[0][i] * wyd[j];
+        const f2 WIJ = dup2(wij);
+        Vxy = fma2(WIJ, s0, Vxy);
+        vz = fmaf(wij, s0z, vz);
+        B0xy = fma2(dup2(wdx), s0, B0xy);
+        B0z = fmaf(wdx, s0z, B0z);
+        B1xy = fma2(dup2(wdy), s0, B1xy);
+        B1z = fmaf(wdy, s0z, B1z);
+        B2xy = fma2(WIJ, s1, B2xy);
+        B2z = fmaf(wij, s1z, B2z);
       }
     }
-  }
-#else
-  // Separable accumulation: for each (i,j) row, s0 = sum_k wz_k v_k and s1 = sum_k wz_k dz_k v_k
-  // (the three k-nodes are one contiguous 48 B run), then one rank-1 update per row.  Nodes
-  // outside the domain / slab load as zero instead of branching.
-  float wzd[3], wxd[3], wyd[3];
+    v[0] = lo2(Vxy); v[1] = hi2(Vxy); v[2] = vz;
+    B.m[0][0] = lo2(B0xy); B.m[1][0] = hi2(B0xy); B.m[2][0] = B0z;
+    B.m[0][1] = lo2(B1xy); B.m[1][1] = hi2(B1xy); B.m[2][1] = B1z;
+    B.m[0][2] = lo2(B2xy); B.m[1][2] = hi2(B2xy); B.m[2][2] = B2z;
+  } else {
+    const G2pGather o = g2p_gather_clipped(grid, k, x[0], x[1], x[2]);
 #pragma unroll
-  for (int q = 0; q < 3; ++q) {
-    wxd[q] = w[0][q] * d[0][q];
-    wyd[q] = w[1][q] * d[1][q];
-    wzd[q] = w[2][q] * d[2][q];
-  }
+    for (int c = 0; c < 3; ++c) {
+      v[c] = o.v[c];
 #pragma unroll
-  for (int i = 0; i < 3; ++i) {
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      const float4* row = gbase + ((long long)i * NN + (long long)j * k.N);
-      const bool okr = ok[0][i] && ok[1][j];
-      float s0[3] = {0.f, 0.f, 0.f}, s1[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-      for (int kz = 0; kz < 3; ++kz) {
-        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (okr && ok[2][kz]) g = __ldg(row + kz);
-        s0[0] += w[2][kz] * g.x; s0[1] += w[2][kz] * g.y; s0[2] += w[2][kz] * g.z;
-        s1[0] += wzd[kz] * g.x;  s1[1] += wzd[kz] * g.y;  s1[2] += wzd[kz] * g.z;
-      }
-      const float wij = w[0][i] * w[1][j];
-      const float wdx = wxd[i] * w[1][j];
-      const float wdy = w[0][i] * wyd[j];
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        v[c] += wij * s0[c];
-        B.m[c][0] += wdx * s0[c];
-        B.m[c][1] += wdy * s0[c];
-        B.m[c][2] += wij * s1[c];
-      }
+      for (int a = 0; a < 3; ++a) B.m[c][a] = o.B[c][a];
     }
   }
-#endif
   Mat3 C, G;
 #pragma unroll
   for (int r = 0; r < 3; ++r)
@@ -374,31 +441,28 @@ g2p_kernel(Soa p, size_t count, const MpmMaterial* __restrict__ mats, const floa
     for (int c = 0; c < 3; ++c) {
       C.m[r][c] = B.m[r][c] * k.dinv;
       G.m[r][c] = ((r == c) ? 1.0f : 0.0f) + k.dt * C.m[r][c];
-    }
 #if !MPM_G2P_PREFETCH
-#pragma unroll
-  for (int r = 0; r < 3; ++r)
-#pragma unroll
-    for (int c = 0; c < 3; ++c) F.m[r][c] = p.s(SF + 3 * r + c)[pi];
+      F.m[r][c] = MPM_LDP(p.s(SF + 3 * r + c) + pi);
 #endif
+    }
   F = mul_ab(G, F);  // F <- (I + dt C) F
   if (MODEL == MPM_MODEL_SNOW) {
-    float Jp = p.s(SJ)[pi];
+    float Jp = MPM_LDP(p.s(SJ) + pi);
     const MpmMaterial m = load_material(mats, p.mat[pi]);
     snow_plasticity<O>(F, Jp, m);
-    p.s(SJ)[pi] = Jp;
+    MPM_STP(p.s(SJ) + pi, Jp);
   }
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
-    p.s(SX + a)[pi] = x[a] + k.dt * v[a];
-    p.s(SV + a)[pi] = v[a];
+    MPM_STP(p.s(SX + a) + pi, x[a] + k.dt * v[a]);
+    MPM_STP(p.s(SV + a) + pi, v[a]);
   }
 #pragma unroll
   for (int r = 0; r < 3; ++r)
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      p.s(SF + 3 * r + c)[pi] = F.m[r][c];
-      p.s(SC + 3 * r + c)[pi] = C.m[r][c];
+      MPM_STP(p.s(SF + 3 * r + c) + pi, F.m[r][c]);
+      MPM_STP(p.s(SC + 3 * r + c) + pi, C.m[r][c]);
     }
 }
 

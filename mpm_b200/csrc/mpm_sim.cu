@@ -1,11 +1,13 @@
 // C ABI of the B200-native MLS-MPM substep: handle, buffers, stage launches.
 // Replaces the device side of the reference's Simulation class (src/mpm.cu:180-329).
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -13,10 +15,13 @@
 #include "../../include/mpm_b200.h"
 #include "comm.cuh"
 #include "kernels.cuh"
+#include "g2p_tile.cuh"
 #include "p2g_runs.cuh"
 #include "sort.cuh"
 
 using namespace mpm;
+
+constexpr int kLtSmall = 48, kLtLarge = 96;  // box lengths the staged kernels are instantiated for
 
 static thread_local std::string g_create_error;
 
@@ -24,6 +29,7 @@ struct MpmSim {
   MpmParams par{};
   KParams k{};
   int device = 0;
+  int n_sms = 148;
   cudaStream_t stream = nullptr;
 
   // particles: two SoA buffers (sort permutes from one into the other)
@@ -51,6 +57,24 @@ struct MpmSim {
   int ghost = 0;
   bool whole_domain = true;
   int sorted_cur = 0;  // which keys[] buffer holds the keys of the current order
+  // particle tiles of the staged kernels (tiles.cuh), rebuilt at every re-bin
+  TileDesc* tiles = nullptr;
+  size_t tiles_cap = 0;
+  uint32_t* row_first = nullptr;  // n_rows + 1
+  uint32_t* tile_base = nullptr;  // n_rows + 1
+  uint32_t* d_n_tiles = nullptr;
+  uint32_t n_rows = 0;
+  // box length (nodes along z) of the staged kernels, chosen from the measured cell span of the
+  // tiles at the last re-bin (read back asynchronously, never waited for)
+  int tile_lt = kLtLarge;
+  unsigned int* d_span = nullptr;  // [0] tiles whose box fits kLtSmall, [1] tiles
+  unsigned int* h_span = nullptr;  // pinned mirror
+  cudaEvent_t span_ev = nullptr;
+  bool span_pending = false;
+  // TMA descriptors: grid as [nxl][N][N][4 floats] with a 5 x 5 x LT box; particle streams of
+  // each SoA buffer as [NSTREAM][stride] with kTile-column boxes of 12 / 13 / 25 rows
+  CUtensorMap tm_grid[2];         // kLtSmall, kLtLarge
+  CUtensorMap tm_streams[2][3];   // [soa buffer][12, 13, 25 rows]
 
   MpmParticle* aos_stage = nullptr;  // device AoS staging for upload/download
   size_t aos_stage_cap = 0;
@@ -89,6 +113,56 @@ int fail(MpmSim* s, const char* fmt, ...) {
 
 inline unsigned blocks_for(size_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+int make_stream_maps(MpmSim* sim, int buf) {
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) return fail(sim, "cuTensorMapEncodeTiled is not available from this driver");
+  const Soa& s = sim->soa[buf];
+  const int rows[3] = {12, 13, NSTREAM};
+  for (int r = 0; r < 3; ++r) {
+    const cuuint64_t dims[2] = {(cuuint64_t)s.stride, (cuuint64_t)NSTREAM};
+    const cuuint64_t strides[1] = {(cuuint64_t)s.stride * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)kTile, (cuuint32_t)rows[r]};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult rc = enc(&sim->tm_streams[buf][r], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, s.f, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) return fail(sim, "cuTensorMapEncodeTiled(streams) failed: %d", (int)rc);
+  }
+  return 0;
+}
+
+int make_grid_maps(MpmSim* sim) {
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) return fail(sim, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t N = (cuuint64_t)sim->k.N;
+  const int lts[2] = {kLtSmall, kLtLarge};
+  for (int i = 0; i < 2; ++i) {
+    const cuuint64_t dims[4] = {4, N, N, (cuuint64_t)sim->k.nxl};
+    const cuuint64_t strides[3] = {16, 16 * N, 16 * N * N};
+    const cuuint32_t box[4] = {4, (cuuint32_t)lts[i], 5, 5};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult rc = enc(&sim->tm_grid[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, sim->grid, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) return fail(sim, "cuTensorMapEncodeTiled(grid) failed: %d", (int)rc);
+  }
+  return 0;
+}
+
 int alloc_soa(MpmSim* sim, Soa& s, size_t cap) {
   s.stride = (cap + 31) / 32 * 32;
   CK(cudaMalloc(&s.f, sizeof(float) * NSTREAM * s.stride));
@@ -113,12 +187,16 @@ int ensure_capacity(MpmSim* sim, size_t cap) {
     }
     cudaFree(sim->table);
     cudaFree(sim->scan_sums);
+    cudaFree(sim->tiles);
   }
   for (int b = 0; b < 2; ++b) {
     if (int rc = alloc_soa(sim, sim->soa[b], cap)) return rc;
+    if (int rc = make_stream_maps(sim, b)) return rc;
     CK(cudaMalloc(&sim->keys[b], sizeof(uint32_t) * cap));
     CK(cudaMalloc(&sim->vals[b], sizeof(uint32_t) * cap));
   }
+  sim->tiles_cap = cap / kTileMax + sim->n_rows + 1;  // every row adds at most one partial tile
+  CK(cudaMalloc(&sim->tiles, sizeof(TileDesc) * sim->tiles_cap));
   const size_t n_tiles = (cap + kSortTile - 1) / kSortTile;
   sim->table_len = n_tiles * kRadix;
   CK(cudaMalloc(&sim->table, sizeof(uint32_t) * sim->table_len));
@@ -156,6 +234,23 @@ struct StageTimer {
 };
 
 // ---- stages -------------------------------------------------------------------------------------
+// tile descriptors of the current (freshly sorted) order, from keys[sorted_cur]
+int build_tiles(MpmSim* sim) {
+  const uint32_t* keys = sim->keys[sim->sorted_cur];
+  const uint32_t n_rows = sim->n_rows;
+  row_bounds_kernel<<<blocks_for((size_t)n_rows + 1, 256), 256, 0, sim->stream>>>(keys, (uint32_t)sim->count, (uint32_t)sim->k.N, n_rows,
+                                                                                  sim->row_first);
+  row_tiles_scan_kernel<<<1, 1024, 0, sim->stream>>>(sim->row_first, n_rows, sim->tile_base, sim->d_n_tiles);
+  CK(cudaMemsetAsync(sim->d_span, 0, 2 * sizeof(unsigned int), sim->stream));
+  tile_fill_kernel<<<blocks_for(n_rows, 256), 256, 0, sim->stream>>>(keys, sim->row_first, sim->tile_base, n_rows, sim->tiles, kLtSmall,
+                                                                     sim->d_span);
+  sim->launches += 3;
+  CK(cudaMemcpyAsync(sim->h_span, sim->d_span, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, sim->stream));
+  CK(cudaEventRecord(sim->span_ev, sim->stream));
+  sim->span_pending = true;
+  return 0;
+}
+
 int do_sort(MpmSim* sim) {
   StageTimer tm(sim, MPM_STAGE_SORT);
   sim->steps_since_sort = 0;
@@ -165,7 +260,10 @@ int do_sort(MpmSim* sim) {
       return fail(sim, "particle migration failed: %s", sim->comm.error());
   }
   const size_t n = sim->count;
-  if (n == 0) return 0;
+  if (n == 0) {
+    CK(cudaMemsetAsync(sim->d_n_tiles, 0, sizeof(uint32_t), sim->stream));
+    return 0;
+  }
   Soa& src = sim->soa[sim->cur];
   const uint32_t dead_key = 1u << sim->key_bits;
   const int sort_bits = sim->key_bits + (sim->comm.active() ? 1 : 0);
@@ -191,6 +289,7 @@ int do_sort(MpmSim* sim) {
   sim->launches++;
   sim->cur ^= 1;
   sim->count = n - n_dead;  // tombstones were sorted behind the live particles
+  if (int rc = build_tiles(sim)) return rc;
   CK(cudaGetLastError());
   return 0;
 }
@@ -238,9 +337,41 @@ int do_grid(MpmSim* sim) {
   return 0;
 }
 
+template <int MODEL, class O, int LT>
+void launch_g2p_tile(MpmSim* sim) {
+  const size_t smem = G2pTileLayout<MODEL>::bytes(LT);
+  static int per_sm = 0;  // per instantiation
+  if (!per_sm) {
+    cudaFuncSetAttribute(g2p_tile_kernel<MODEL, O, LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, g2p_tile_kernel<MODEL, O, LT>, kG2pThreads, smem);
+    per_sm = std::max(per_sm, 1);
+  }
+  const size_t max_tiles = sim->count / kTileMax + sim->n_rows + 1;
+  const unsigned ctas = (unsigned)std::min<size_t>(max_tiles, (size_t)sim->n_sms * per_sm);
+  g2p_tile_kernel<MODEL, O, LT><<<ctas, kG2pThreads, smem, sim->stream>>>(
+      sim->soa[sim->cur], sim->mats, sim->grid, sim->k, sim->tiles, sim->d_n_tiles, sim->tm_grid[LT == kLtSmall ? 0 : 1],
+      sim->tm_streams[sim->cur][MODEL == MPM_MODEL_SNOW ? 1 : 0]);
+}
+
 template <int MODEL>
 int launch_g2p(MpmSim* sim) {
   const size_t n = sim->count;
+  if (sim->par.g2p_mode == MPM_G2P_TILE) {
+    if (sim->span_pending && cudaEventQuery(sim->span_ev) == cudaSuccess) {
+      sim->span_pending = false;
+      // the small box when (nearly) every tile fits it; particles beyond the box take the
+      // global-memory gather, which is correct but slow
+      sim->tile_lt = (sim->h_span[1] && (double)sim->h_span[0] >= 0.95 * (double)sim->h_span[1]) ? kLtSmall : kLtLarge;
+    }
+    if (const char* e = getenv("MPM_TILE_LT")) sim->tile_lt = atoi(e) == kLtSmall ? kLtSmall : kLtLarge;  // experiments only
+    const bool exact = sim->par.svd_mode == MPM_SVD_EXACT;
+    if (sim->tile_lt == kLtSmall) {
+      if (exact) launch_g2p_tile<MODEL, ExactOps, kLtSmall>(sim); else launch_g2p_tile<MODEL, FastOps, kLtSmall>(sim);
+    } else {
+      if (exact) launch_g2p_tile<MODEL, ExactOps, kLtLarge>(sim); else launch_g2p_tile<MODEL, FastOps, kLtLarge>(sim);
+    }
+    return 0;
+  }
   const unsigned nb = blocks_for(n, kG2pBlock);
   Soa& p = sim->soa[sim->cur];
   if (sim->par.svd_mode == MPM_SVD_EXACT)
@@ -289,8 +420,9 @@ int mpm_create(const MpmParams* params, const MpmMaterial* materials, int n_mate
   if (!params || !out) return fail(nullptr, "mpm_create: null argument");
   if (params->N < 4) return fail(nullptr, "mpm_create: N must be >= 4");
   if (n_materials < 1 || n_materials > 256 || !materials) return fail(nullptr, "mpm_create: need 1..256 materials");
-  if (params->model > MPM_MODEL_FIXED_COROTATED || params->svd_mode > MPM_SVD_FAST || params->p2g_mode > MPM_P2G_DIRECT)
-    return fail(nullptr, "mpm_create: bad model / svd_mode / p2g_mode");
+  if (params->model > MPM_MODEL_FIXED_COROTATED || params->svd_mode > MPM_SVD_FAST || params->p2g_mode > MPM_P2G_DIRECT ||
+      params->g2p_mode > MPM_G2P_DIRECT || params->reserved_ != 0)
+    return fail(nullptr, "mpm_create: bad model / svd_mode / p2g_mode / g2p_mode");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -315,6 +447,7 @@ int mpm_create(const MpmParams* params, const MpmMaterial* materials, int n_mate
   CKC(cudaSetDevice(sim->device));
   cudaDeviceProp prop;
   CKC(cudaGetDeviceProperties(&prop, sim->device));
+  sim->n_sms = prop.multiProcessorCount;
   if (prop.major < 10) {
     fail(nullptr, "mpm_create: device %d is sm_%d%d; this library is built for sm_100a only", sim->device, prop.major, prop.minor);
     mpm_destroy(sim);
@@ -341,6 +474,7 @@ int mpm_create(const MpmParams* params, const MpmMaterial* materials, int n_mate
   k.x0 = std::max(0, xb - sim->ghost);
   k.nxl = std::min(N, xe + 2 + sim->ghost) - k.x0;  // owned + 2 stencil planes above + ghost planes either side
   sim->grid_nodes = (size_t)k.nxl * N * N;
+  sim->n_rows = (uint32_t)k.nxl * (uint32_t)N;
   sim->key_bits = bits_for(sim->grid_nodes);
   CKC(cudaStreamCreateWithFlags(&sim->stream, cudaStreamNonBlocking));
   CKC(cudaEventCreate(&sim->ev[0]));
@@ -351,6 +485,18 @@ int mpm_create(const MpmParams* params, const MpmMaterial* materials, int n_mate
   CKC(cudaMalloc(&sim->mats, sizeof(MpmMaterial) * n_materials));
   CKC(cudaMemcpy(sim->mats, materials, sizeof(MpmMaterial) * n_materials, cudaMemcpyHostToDevice));
   CKC(cudaMalloc(&sim->d_counter, sizeof(unsigned long long)));
+  CKC(cudaMalloc(&sim->row_first, sizeof(uint32_t) * ((size_t)sim->n_rows + 1)));
+  CKC(cudaMalloc(&sim->tile_base, sizeof(uint32_t) * ((size_t)sim->n_rows + 1)));
+  CKC(cudaMalloc(&sim->d_n_tiles, sizeof(uint32_t)));
+  CKC(cudaMemsetAsync(sim->d_n_tiles, 0, sizeof(uint32_t), sim->stream));
+  if (make_grid_maps(sim)) {
+    g_create_error = sim->err;
+    mpm_destroy(sim);
+    return 1;
+  }
+  CKC(cudaMalloc(&sim->d_span, 2 * sizeof(unsigned int)));
+  CKC(cudaMallocHost(&sim->h_span, 2 * sizeof(unsigned int)));
+  CKC(cudaEventCreateWithFlags(&sim->span_ev, cudaEventDisableTiming));
   if (params->capacity) {
     if (int rc = ensure_capacity(sim, (size_t)params->capacity)) {
       g_create_error = sim->err;
@@ -379,6 +525,13 @@ void mpm_destroy(MpmSim* sim) {
   cudaFree(sim->mats);
   cudaFree(sim->aos_stage);
   cudaFree(sim->d_counter);
+  cudaFree(sim->d_span);
+  cudaFree(sim->tiles);
+  cudaFree(sim->row_first);
+  cudaFree(sim->tile_base);
+  cudaFree(sim->d_n_tiles);
+  if (sim->h_span) cudaFreeHost(sim->h_span);
+  if (sim->span_ev) cudaEventDestroy(sim->span_ev);
   if (sim->ev[0]) cudaEventDestroy(sim->ev[0]);
   if (sim->ev[1]) cudaEventDestroy(sim->ev[1]);
   if (sim->stream) cudaStreamDestroy(sim->stream);
@@ -530,6 +683,19 @@ int mpm_debug_upload_grid(MpmSim* sim, const float* vec4, size_t n_nodes) {
   CK(cudaSetDevice(sim->device));
   if (n_nodes != sim->grid_nodes) return fail(sim, "grid has %zu nodes, caller passed %zu", sim->grid_nodes, n_nodes);
   CK(cudaMemcpyAsync(sim->grid, vec4, sizeof(float4) * n_nodes, cudaMemcpyHostToDevice, sim->stream));
+  CK(cudaStreamSynchronize(sim->stream));
+  return 0;
+}
+int mpm_debug_overwrite_particles_aos(MpmSim* sim, const MpmParticle* particles, size_t count) {
+  if (!sim || !particles) return 1;
+  CK(cudaSetDevice(sim->device));
+  if (count != sim->count || !sim->whole_domain) return fail(sim, "overwrite needs the same particle count on a whole-domain handle");
+  if (count == 0) return 0;
+  if (int rc = ensure_stage(sim, count)) return rc;
+  CK(cudaMemcpyAsync(sim->aos_stage, particles, sizeof(MpmParticle) * count, cudaMemcpyHostToDevice, sim->stream));
+  aos_overwrite_kernel<<<blocks_for(count, 256), 256, 0, sim->stream>>>(sim->aos_stage, sim->soa[sim->cur], count, sim->first_id);
+  sim->launches++;
+  CK(cudaGetLastError());
   CK(cudaStreamSynchronize(sim->stream));
   return 0;
 }

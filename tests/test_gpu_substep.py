@@ -96,11 +96,12 @@ def test_grid_update_matches_oracle():
 
 @pytest.mark.parametrize("kind", [ol.SNOW, ol.FIXED_COROTATED])
 @pytest.mark.parametrize("mode", MODES)
-def test_g2p_single_step_from_identical_grid(kind, mode):
+@pytest.mark.parametrize("g2p_mode", [0, 1])  # MPM_G2P_TILE, MPM_G2P_DIRECT
+def test_g2p_single_step_from_identical_grid(kind, mode, g2p_mode):
     N = 32
     p, mats = scenes.two_spheres(N, kind=kind)
     go = ol.grid_update(ol.p2g(p, mats, DT, N, kind), DT, N)
-    sim = _sim(N, mats, kind, mode)
+    sim = _sim(N, mats, kind, mode, g2p_mode=g2p_mode)
     sim.upload(p)
     sim.set_grid(go)
     sim.stage("g2p")
@@ -119,11 +120,14 @@ def test_g2p_single_step_from_identical_grid(kind, mode):
 
 @pytest.mark.parametrize("kind,steps", [(ol.SNOW, 100), (ol.FIXED_COROTATED, 100)])
 @pytest.mark.parametrize("mode", MODES)
-def test_short_horizon_against_oracle(kind, steps, mode):
-    """100 substeps of a two-ball impact: per-particle position / velocity error, mass, momentum."""
+@pytest.mark.parametrize("sort_every,g2p_mode", [(10, 0), (0, 0), (10, 1)])
+def test_short_horizon_against_oracle(kind, steps, mode, sort_every, g2p_mode):
+    """100 substeps of a two-ball impact: per-particle position / velocity error, mass, momentum.
+    sort_every=0 never re-bins after the upload: the thrown ball drifts ~1 cell, so the staged
+    kernels see particles in neighbouring window rows and beyond (their global-memory path)."""
     N = 32
     p, mats = scenes.two_spheres(N, kind=kind, perturb=False)
-    sim = _sim(N, mats, kind, mode, sort_every=10)
+    sim = _sim(N, mats, kind, mode, sort_every=sort_every, g2p_mode=g2p_mode)
     sim.upload(p)
     sim.advance(steps)
     got = sim.download()
@@ -136,6 +140,37 @@ def test_short_horizon_against_oracle(kind, steps, mode):
     mom_g = got["v"].astype(np.float64).sum(0)
     mom_r = ref["v"].astype(np.float64).sum(0)
     assert np.abs(mom_g - mom_r).max() <= 1e-4 * np.abs(ref["v"]).astype(np.float64).sum()
+
+
+def test_g2p_tile_handles_stale_order_and_domain_faces():
+    """The staged G2P against the direct one from the same grid: particles scattered over the whole
+    domain (clipped stencils at the faces, out-of-domain particles) and an order made stale by
+    moving every particle up to 2.5 cells after the re-bin, so all of the window rows (di, dj in
+    -1..1), the slack along z and the out-of-window path are exercised."""
+    N = 32
+    rng = np.random.default_rng(11)
+    n = 40_000
+    x0 = rng.uniform(-0.02, 1.02, (n, 3)).astype(np.float32)
+    p = ol.new_particles(x0)
+    p["F"] += 0.02 * rng.standard_normal(p["F"].shape).astype(np.float32)
+    mats = ol.make_material(1.0 / 200000.0)
+    g = rng.standard_normal((N, N, N, 4)).astype(np.float32)
+    g[..., 3] = np.abs(g[..., 3])
+    moved = p.copy()
+    moved["x"] = x0 + rng.uniform(-2.5 / N, 2.5 / N, (n, 3)).astype(np.float32)
+    out = []
+    for g2p_mode in (0, 1):
+        sim = _sim(N, mats, ol.SNOW, 0, g2p_mode=g2p_mode)
+        sim.upload(p)          # bins by x0
+        sim.overwrite(moved)   # same slots, new positions: the order and the key array are now stale
+        sim.set_grid(g)
+        sim.stage("g2p")
+        out.append(sim.download())
+    a, b = out
+    for f in ("x", "v", "F", "C", "Jp"):
+        assert np.allclose(a[f], b[f], rtol=2e-5, atol=2e-5 * np.abs(b[f]).max()), f
+    ref = ol.g2p(g, moved.copy(), mats, DT, N, ol.SNOW)
+    assert np.allclose(a["v"], ref["v"], rtol=1e-4, atol=1e-4)
 
 
 def test_free_fall_velocity():
