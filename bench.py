@@ -158,6 +158,8 @@ def main():
     ap.add_argument("--sort-every", type=int, default=8)
     ap.add_argument("--svd", default="fast", choices=["fast", "exact"])
     ap.add_argument("--particles", type=int, default=P_PER_GPU, help="particles per GPU (default 2^26)")
+    ap.add_argument("--g2p", default="tile", choices=["tile", "direct"], help="G2P kernel (MpmParams.g2p_mode)")
+    ap.add_argument("--p2g", default="runs", choices=["runs", "direct"], help="P2G kernel (MpmParams.p2g_mode)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -196,7 +198,9 @@ def main():
     svd_mode = mpm_b200.SVD_FAST if args.svd == "fast" else mpm_b200.SVD_EXACT
     cap = int(args.particles * 1.15) if world > 1 else 0
     sim = mpm_b200.Sim(N, dt, mats, model=mpm_b200.FIXED_COROTATED, svd_mode=svd_mode, sort_every=args.sort_every,
-                       x_begin=xb, x_end=xe, device=local_rank, capacity=cap)
+                       x_begin=xb, x_end=xe, device=local_rank, capacity=cap,
+                       p2g_mode=mpm_b200.P2G_RUNS if args.p2g == "runs" else mpm_b200.P2G_DIRECT,
+                       g2p_mode=mpm_b200.G2P_TILE if args.g2p == "tile" else mpm_b200.G2P_DIRECT)
     if world > 1:
         from mpm_b200 import slabs as _slabs
 
@@ -293,7 +297,7 @@ def main():
             "config": {"workload": f"synthetic dense block N={N}, {int(P_all)} particles, fixed-corotated (BASELINE.json configs[3]"
                                    + (")" if world == 1 else f" scaled weakly to {world} GPUs: 2^26 particles and ~2^24 nodes per GPU)"),
                        "N": N, "particles": int(P_all), "grid_nodes": int(G_all), "dt": dt, "model": "fixed_corotated",
-                       "svd_mode": args.svd, "sort_every": args.sort_every, "slabs": slabs if world > 1 else None,
+                       "svd_mode": args.svd, "sort_every": args.sort_every, "p2g": args.p2g, "g2p": args.g2p, "slabs": slabs if world > 1 else None,
                        "l2": "inputs (6.7 GB particles + 268 MB grid per GPU) are far larger than the 126 MB L2; no flush"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "substep_roofline": substep_roofline, "stage_ms": stage_ms,

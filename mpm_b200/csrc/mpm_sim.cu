@@ -16,7 +16,7 @@
 #include "comm.cuh"
 #include "kernels.cuh"
 #include "g2p_tile.cuh"
-#include "p2g_runs.cuh"
+#include "p2g_sched.cuh"
 #include "sort.cuh"
 
 using namespace mpm;
@@ -44,6 +44,7 @@ struct MpmSim {
   size_t grid_nodes = 0;
 
   MpmMaterial* mats = nullptr;
+  MpmMaterial mat0{};  // host copy of material 0: single-material handles pass it as a kernel parameter
   int n_mats = 0;
 
   // sort scratch
@@ -300,16 +301,22 @@ int do_reset(MpmSim* sim) {
   return 0;
 }
 
+template <int MODEL, class O, bool EXACT>
+void launch_p2g_sched(MpmSim* sim) {
+  const size_t n = sim->count;
+  const unsigned nbr = blocks_for(n, kP2gBlock);
+  if (sim->n_mats == 1)
+    p2g_sched_kernel<MODEL, O, EXACT, true><<<nbr, kP2gBlock, 0, sim->stream>>>(sim->soa[sim->cur], n, sim->mats, sim->mat0, sim->grid, sim->k);
+  else
+    p2g_sched_kernel<MODEL, O, EXACT, false><<<nbr, kP2gBlock, 0, sim->stream>>>(sim->soa[sim->cur], n, sim->mats, sim->mat0, sim->grid, sim->k);
+}
+
 template <int MODEL>
 int launch_p2g(MpmSim* sim) {
   const size_t n = sim->count;
   Soa& p = sim->soa[sim->cur];
   if (sim->par.p2g_mode == MPM_P2G_RUNS && sim->k.N + kKeyBias <= 1023) {
-    const unsigned nbr = blocks_for(n, kP2gBlock);
-    if (sim->par.svd_mode == MPM_SVD_EXACT)
-      p2g_runs_kernel<MODEL, ExactOps, true><<<nbr, kP2gBlock, 0, sim->stream>>>(p, n, sim->mats, sim->grid, sim->k);
-    else
-      p2g_runs_kernel<MODEL, FastOps, false><<<nbr, kP2gBlock, 0, sim->stream>>>(p, n, sim->mats, sim->grid, sim->k);
+    if (sim->par.svd_mode == MPM_SVD_EXACT) launch_p2g_sched<MODEL, ExactOps, true>(sim); else launch_p2g_sched<MODEL, FastOps, false>(sim);
     return 0;
   }
   const unsigned nb = blocks_for(n, kParticleBlock);
@@ -482,6 +489,7 @@ int mpm_create(const MpmParams* params, const MpmMaterial* materials, int n_mate
   CKC(cudaMalloc(&sim->grid, sizeof(float4) * sim->grid_nodes));
   CKC(cudaMemsetAsync(sim->grid, 0, sizeof(float4) * sim->grid_nodes, sim->stream));
   sim->n_mats = n_materials;
+  sim->mat0 = materials[0];
   CKC(cudaMalloc(&sim->mats, sizeof(MpmMaterial) * n_materials));
   CKC(cudaMemcpy(sim->mats, materials, sizeof(MpmMaterial) * n_materials, cudaMemcpyHostToDevice));
   CKC(cudaMalloc(&sim->d_counter, sizeof(unsigned long long)));

@@ -1,0 +1,257 @@
+// Stage (2), production kernel: P2G with in-register pre-reduction of same-cell particle runs and
+// a length-sorted schedule (reference behaviour: src/mpm.cu:14-74, TransferScheme.h:66-100).
+//
+// The direct scatter (p2g_kernel, kernels.cuh) is bound by reduction lanes: 27 REDG per particle.
+// Particles are cell-sorted, so consecutive particles mostly share the base node and therefore all
+// 27 target nodes.  Per block of kP2gBlock consecutive particles:
+//   phase 0  one thread per particle: load the 25 streams (coalesced), stress via polar/svd3,
+//            affine matrix; write a 16-float payload (fractional position, mass, m v + A d at the
+//            base node, dx*A columns) to shared memory.
+//   phase R  warp-local run detection with ballots: a run = maximal stretch of consecutive
+//            particles OF ONE WARP with equal base node (<= 32 particles).  Every run head drops
+//            its run into a histogram bin by length (one shared-memory integer atomic); after one
+//            barrier every warp scans the 32 bins in registers and the heads write the block's run
+//            list in order of DESCENDING LENGTH.
+//   phase 1  three threads per run, one per stencil x-slab (9 nodes, 36 accumulators in
+//            registers), taken from the sorted list: the 32 lanes of a warp get runs of (nearly)
+//            equal length, so the accumulation loop does not diverge — with runs in memory order
+//            a warp waits for its longest run and half the issue slots are lost
+//            (profiles/r01_ncu_v2_runs_p2g.txt).  Then ONE red.global.add.v4.f32 per node per run.
+// Correctness does not depend on the order being perfectly sorted (a stale order only shortens
+// the runs).
+#pragma once
+#include "common.cuh"
+
+namespace mpm {
+
+#ifndef MPM_P2G_MINBLK
+#define MPM_P2G_MINBLK 3
+#endif
+constexpr int kP2gBlock = 256;
+constexpr uint32_t kInvalidKey = 0xffffffffu;
+constexpr int kKeyBias = 4;  // base node >= -3 for particles that are not skipped
+
+struct P2gSmem {
+  // per-particle payload record, 4 x float4 used of a 5 x float4 (80 B) stride: consecutive
+  // records start 20 banks apart, so the 128-bit reads of 8 different runs are conflict-free
+  //   [0] = (fx, fy, fz, mass)  [1] = (q0.xyz, cx.x)  [2] = (cx.y, cx.z, cy.x, cy.y)  [3] = (cy.z, cz.xyz)
+  float4 pay[kP2gBlock][5];
+  uint32_t key[kP2gBlock];
+  uint32_t hist[32];          // bin b = runs of length 32 - b
+  uint16_t runs[kP2gBlock];   // first particle | (length - 1) << 8, longest first
+};
+
+// what phase 0 hands to phase 1 for one particle
+struct P2gPayload {
+  float f[3];      // fractional position relative to the base node, in cells: [0.5, 1.5)
+  float mass;
+  float q0[3];     // m v + A (x_base - x)
+  float cx[3], cy[3], cz[3];  // dx * A columns: the change of q per node step along x, y, z
+  uint32_t key;    // packed biased base node, kInvalidKey for a particle outside the domain
+};
+
+// P2G particle preparation (reference TransferScheme.h:66-86 + MaterialModel.cuh:85-93), folded:
+//   A = -Dinv dt vol PF + m C,  PF = 2 mu (F - R) F^T + lambda (Jp - 1) Jp I
+//   q(node) = m v + A (x_node - x) = q0 + i cx + j cy + k cz,  x_base - x = -dx f
+template <int MODEL, class O, bool EXACT>
+__device__ __forceinline__ P2gPayload p2g_prepare(const float x[3], const float v[3], const Mat3& F, const Mat3& C, float Jp,
+                                                  const MpmMaterial& m, const KParams& k) {
+  P2gPayload o;
+  int base[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float g = x[a] * k.dx_inv;
+    base[a] = (int)(g - 0.5f);  // C truncation like the reference's cast<int>()
+    o.f[a] = g - (float)base[a];
+  }
+  bool inside = true;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) inside = inside && !(base[a] + 3 < 0 || base[a] >= k.N);  // src/mpm.cu:31-35
+  o.key = inside ? (((uint32_t)(base[0] + kKeyBias) << 20) | ((uint32_t)(base[1] + kKeyBias) << 10) | (uint32_t)(base[2] + kKeyBias))
+                 : kInvalidKey;
+  Mat3 R;
+  if constexpr (EXACT) R = polar_rotation<O>(F); else R = polar_rotation_newton(F);
+  float mu = m.mu0, lambda = m.lambda0;
+  if (MODEL == MPM_MODEL_SNOW) {
+    float e;
+    if (EXACT) e = (float)exp((double)m.hardening * (1.0 - (double)Jp));
+    else e = (m.hardening == 0.0f) ? 1.0f : __expf(m.hardening * (1.0f - Jp));
+    mu *= e;
+    lambda *= e;
+  }
+  float lam_term;
+  if (EXACT) lam_term = (float)((double)lambda * (((double)Jp - 1.0) * (double)Jp));
+  else lam_term = lambda * ((Jp - 1.0f) * Jp);
+  const float kk = (((-k.dinv) * k.dt) * m.particleVolume) * k.dx;  // -Dinv dt vol, times dx for the columns
+  const float s_dev = kk * (2.0f * mu), s_vol = kk * lam_term, s_c = m.particleMass * k.dx;
+  Mat3 D;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) D.m[i][j] = F.m[i][j] - R.m[i][j];
+  const Mat3 M = mul_abt(D, F);  // (F - R) F^T
+  float Ad[3][3];                // dx * A
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) Ad[i][j] = fmaf(s_dev, M.m[i][j], s_c * C.m[i][j]) + ((i == j) ? s_vol : 0.0f);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    o.cx[c] = Ad[c][0];
+    o.cy[c] = Ad[c][1];
+    o.cz[c] = Ad[c][2];
+    o.q0[c] = v[c] * m.particleMass - (Ad[c][0] * o.f[0] + Ad[c][1] * o.f[1] + Ad[c][2] * o.f[2]);
+  }
+  o.mass = m.particleMass;
+  return o;
+}
+
+// quadratic B-spline weights from the fractional position (InterpolationKernel.cuh:61-66);
+// w2 = w0 + (f - 1) is the same polynomial with two operations fewer
+__device__ __forceinline__ void bspline_w(float f, float w[3]) {
+  const float a0 = 1.5f - f, a1 = f - 1.0f;
+  w[0] = (0.5f * a0) * a0;
+  w[1] = fmaf(-a1, a1, 0.75f);
+  w[2] = w[0] + a1;
+}
+
+template <int MODEL, class O, bool EXACT, bool ONE_MAT>
+__global__ void __launch_bounds__(kP2gBlock, MPM_P2G_MINBLK)
+p2g_sched_kernel(Soa p, size_t count, const MpmMaterial* __restrict__ mats, const MpmMaterial mat0, float4* __restrict__ grid,
+                 KParams k) {
+  __shared__ P2gSmem sm;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const size_t pi = (size_t)blockIdx.x * kP2gBlock + tid;
+  if (tid < 32) sm.hist[tid] = 0;
+  __syncthreads();
+
+  // ---------------- phase 0: per-particle payload ----------------
+  uint32_t key = kInvalidKey;
+  if (pi < count) {
+    float x[3], v[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      x[a] = p.s(SX + a)[pi];
+      v[a] = p.s(SV + a)[pi];
+    }
+    Mat3 F, C;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        F.m[r][c] = p.s(SF + 3 * r + c)[pi];
+        C.m[r][c] = p.s(SC + 3 * r + c)[pi];
+      }
+    const float Jp = (MODEL == MPM_MODEL_SNOW) ? p.s(SJ)[pi] : 1.0f;  // fixed-corotated never changes Jp
+    MpmMaterial m;
+    if constexpr (ONE_MAT) m = mat0; else m = load_material(mats, p.mat[pi]);  // ONE_MAT: operands straight from the constant bank
+    const P2gPayload o = p2g_prepare<MODEL, O, EXACT>(x, v, F, C, Jp, m, k);
+    key = o.key;
+    sm.pay[tid][0] = make_float4(o.f[0], o.f[1], o.f[2], o.mass);
+    sm.pay[tid][1] = make_float4(o.q0[0], o.q0[1], o.q0[2], o.cx[0]);
+    sm.pay[tid][2] = make_float4(o.cx[1], o.cx[2], o.cy[0], o.cy[1]);
+    sm.pay[tid][3] = make_float4(o.cy[2], o.cz[0], o.cz[1], o.cz[2]);
+  }
+  sm.key[tid] = key;
+
+  // ---------------- phase R: warp-local runs, block-wide list sorted by length ----------------
+  const uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
+  const bool head = (lane == 0) || (prev != key);
+  const uint32_t heads = __ballot_sync(0xffffffffu, head);
+  const uint32_t rest = (lane == 31) ? 0u : (heads >> (lane + 1));
+  const int len = rest ? __ffs(rest) : (32 - lane);  // meaningful for heads
+  const bool listed = head && key != kInvalidKey;     // skipped particles / the tail of the last block scatter nothing
+  uint32_t slot = 0;
+  if (listed) slot = atomicAdd(&sm.hist[32 - len], 1u);
+  __syncthreads();
+  uint32_t incl = sm.hist[lane];
+  const uint32_t cnt = incl;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  const int n_runs = (int)__shfl_sync(0xffffffffu, incl, 31);
+  const uint32_t bin_base = __shfl_sync(0xffffffffu, incl - cnt, listed ? (32 - len) : 0);
+  if (listed) sm.runs[bin_base + slot] = (uint16_t)(tid | ((len - 1) << 8));
+  __syncthreads();
+
+  // ---------------- phase 1: 3 threads per run ----------------
+  const long long NN = (long long)k.N * k.N;
+  const int gx_lo = max(0, k.x0), gx_hi = min(k.N, k.x0 + k.nxl);
+  for (int u = tid; u < 3 * n_runs; u += kP2gBlock) {
+    const int r = u / 3, i = u - 3 * r;
+    const uint32_t run = sm.runs[r];
+    const int s0 = (int)(run & 255u), s1 = s0 + (int)(run >> 8) + 1;
+    const uint32_t rk = sm.key[s0];
+    float4 acc[3][3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+      for (int kz = 0; kz < 3; ++kz) acc[j][kz] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // this thread's x-slab weight as a + b (f - c)^2
+    const float fi = (float)i;
+    const float wc = 1.5f - 0.5f * fi, wa = (i == 1) ? 0.75f : 0.0f, wb = (i == 1) ? -1.0f : 0.5f;
+#pragma unroll 1
+    for (int s = s0; s < s1; ++s) {
+      const float4 r0 = sm.pay[s][0], r1 = sm.pay[s][1], r2 = sm.pay[s][2], r3 = sm.pay[s][3];
+      const float dxi = r0.x - wc;
+      const float wxi = fmaf(wb * dxi, dxi, wa);
+      float wy[3], wz[3];
+      bspline_w(r0.y, wy);
+      bspline_w(r0.z, wz);
+      const float mass = r0.w;
+      float q[3] = {fmaf(fi, r1.w, r1.x), fmaf(fi, r2.x, r1.y), fmaf(fi, r2.y, r1.z)};
+      const float cy[3] = {r2.z, r2.w, r3.x};
+      const float cz[3] = {r3.y, r3.z, r3.w};
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const float wij = wxi * wy[j];
+        float qk[3] = {q[0], q[1], q[2]};
+#pragma unroll
+        for (int kz = 0; kz < 3; ++kz) {
+          const float wt = wij * wz[kz];
+          acc[j][kz].x = fmaf(wt, qk[0], acc[j][kz].x);
+          acc[j][kz].y = fmaf(wt, qk[1], acc[j][kz].y);
+          acc[j][kz].z = fmaf(wt, qk[2], acc[j][kz].z);
+          acc[j][kz].w = fmaf(wt, mass, acc[j][kz].w);
+          if (kz < 2) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) qk[c] += cz[c];
+          }
+        }
+        if (j < 2) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) q[c] += cy[c];
+        }
+      }
+    }
+    // flush: one vector reduction per node of this slab
+    const int bx = (int)(rk >> 20) - kKeyBias, by = (int)((rk >> 10) & 1023u) - kKeyBias, bz = (int)(rk & 1023u) - kKeyBias;
+    const int gx = bx + i;
+    if (gx < gx_lo || gx >= gx_hi) continue;
+    float4* gp = grid + ((long long)(gx - k.x0) * NN + (long long)by * k.N + bz);
+    if ((unsigned)by <= (unsigned)(k.N - 3) && (unsigned)bz <= (unsigned)(k.N - 3)) {  // whole 3 x 3 patch inside
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        float4* row = gp + j * k.N;
+#pragma unroll
+        for (int kz = 0; kz < 3; ++kz) atomicAdd(row + kz, acc[j][kz]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int gy = by + j;
+        if (gy < 0 || gy >= k.N) continue;
+#pragma unroll
+        for (int kz = 0; kz < 3; ++kz) {
+          const int gz = bz + kz;
+          if (gz < 0 || gz >= k.N) continue;
+          atomicAdd(gp + (j * k.N + kz), acc[j][kz]);
+        }
+      }
+    }
+  }
+}
+
+}  // namespace mpm

@@ -348,45 +348,62 @@ __device__ __forceinline__ Mat3 polar_rotation(const Mat3& A) {
 }
 
 // FAST-mode polar rotation: Newton iteration X <- (X + X^-T)/2 (Higham), quadratically convergent
-// and ~45 instructions per step against ~1300 for a full svd3.  It converges to the orthogonal
+// and ~60 instructions per step against ~1300 for a full svd3.  It converges to the orthogonal
 // polar factor, which equals the reference's R = U V^T exactly when det(A) > 0; inverted or
 // near-singular elements (det <= 1e-6 * |A|^3, rare) take the svd3 route so the sign convention of
-// the reference (U, V proper rotations, sigma_3 < 0) is kept.  More accurate than svd3's R
-// (which carries the 4-sweep Jacobi error of ~1e-6); the deviation is reported by the tests.
-__device__ __forceinline__ Mat3 polar_rotation_newton(const Mat3& A) {
-  const float d = det3(A);
-  float n2 = 0.f;
+// the reference (U, V proper rotations, sigma_3 < 0) is kept.  The step size delta_k = |X_k - X_k-1|
+// is the error of X_k-1 and the error of X_k is ~delta_k^2 / 2, so stopping at delta_k < 3e-4 leaves
+// < 5e-8: quiescent material (F = I + O(1e-4)) takes ONE step, snow (strain <= 2.5 %) two.  More
+// accurate than svd3's R (which carries the 4-sweep Jacobi error of ~1e-6); the deviation is
+// reported by the tests.
+__device__ __forceinline__ float rcp_approx(float x) {  // one MUFU.RCP, no denormal/range fix-up
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// cofactor matrix (= det * X^-T) and determinant
+__device__ __forceinline__ float cofactor3(const Mat3& X, Mat3& Cf) {
+  Cf.m[0][0] = X.m[1][1] * X.m[2][2] - X.m[1][2] * X.m[2][1];
+  Cf.m[0][1] = X.m[1][2] * X.m[2][0] - X.m[1][0] * X.m[2][2];
+  Cf.m[0][2] = X.m[1][0] * X.m[2][1] - X.m[1][1] * X.m[2][0];
+  Cf.m[1][0] = X.m[0][2] * X.m[2][1] - X.m[0][1] * X.m[2][2];
+  Cf.m[1][1] = X.m[0][0] * X.m[2][2] - X.m[0][2] * X.m[2][0];
+  Cf.m[1][2] = X.m[0][1] * X.m[2][0] - X.m[0][0] * X.m[2][1];
+  Cf.m[2][0] = X.m[0][1] * X.m[1][2] - X.m[0][2] * X.m[1][1];
+  Cf.m[2][1] = X.m[0][2] * X.m[1][0] - X.m[0][0] * X.m[1][2];
+  Cf.m[2][2] = X.m[0][0] * X.m[1][1] - X.m[0][1] * X.m[1][0];
+  return X.m[0][0] * Cf.m[0][0] + X.m[0][1] * Cf.m[0][1] + X.m[0][2] * Cf.m[0][2];
+}
+// X <- (X + X^-T) / 2; returns max |change|
+__device__ __forceinline__ float polar_newton_step(Mat3& X, const Mat3& Cf, float det) {
+  const float h = 0.5f * rcp_approx(det);
+  float delta = 0.f;
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll
-    for (int j = 0; j < 3; ++j) n2 += A.m[i][j] * A.m[i][j];
-  if (!(d > 1e-6f * n2 * sqrtf(n2))) return polar_rotation<FastOps>(A);
-  Mat3 X = A;
-#pragma unroll 1
-  for (int it = 0; it < 16; ++it) {
-    // cofactor matrix = det * X^-T
-    Mat3 Cf;
-    Cf.m[0][0] = X.m[1][1] * X.m[2][2] - X.m[1][2] * X.m[2][1];
-    Cf.m[0][1] = X.m[1][2] * X.m[2][0] - X.m[1][0] * X.m[2][2];
-    Cf.m[0][2] = X.m[1][0] * X.m[2][1] - X.m[1][1] * X.m[2][0];
-    Cf.m[1][0] = X.m[0][2] * X.m[2][1] - X.m[0][1] * X.m[2][2];
-    Cf.m[1][1] = X.m[0][0] * X.m[2][2] - X.m[0][2] * X.m[2][0];
-    Cf.m[1][2] = X.m[0][1] * X.m[2][0] - X.m[0][0] * X.m[2][1];
-    Cf.m[2][0] = X.m[0][1] * X.m[1][2] - X.m[0][2] * X.m[1][1];
-    Cf.m[2][1] = X.m[0][2] * X.m[1][0] - X.m[0][0] * X.m[1][2];
-    Cf.m[2][2] = X.m[0][0] * X.m[1][1] - X.m[0][1] * X.m[1][0];
-    const float det = X.m[0][0] * Cf.m[0][0] + X.m[0][1] * Cf.m[0][1] + X.m[0][2] * Cf.m[0][2];
-    const float h = 0.5f / det;
-    float delta = 0.f;
+    for (int j = 0; j < 3; ++j) {
+      const float xn = fmaf(h, Cf.m[i][j], 0.5f * X.m[i][j]);
+      delta = fmaxf(delta, fabsf(xn - X.m[i][j]));
+      X.m[i][j] = xn;
+    }
+  return delta;
+}
+__device__ __forceinline__ Mat3 polar_rotation_newton(const Mat3& A) {
+  Mat3 X = A, Cf;
+  float det = cofactor3(X, Cf);
+  {  // det(A) is at hand: the guard costs one norm
+    float n2 = 0.f;
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const float xn = 0.5f * X.m[i][j] + h * Cf.m[i][j];
-        delta = fmaxf(delta, fabsf(xn - X.m[i][j]));
-        X.m[i][j] = xn;
-      }
-    if (delta < 5e-7f) break;  // quadratic convergence: the next step would be ~1e-13
+      for (int j = 0; j < 3; ++j) n2 = fmaf(A.m[i][j], A.m[i][j], n2);
+    if (!(det > 1e-6f * n2 * sqrtf(n2))) return polar_rotation<FastOps>(A);
+  }
+  float delta = polar_newton_step(X, Cf, det);  // peeled: the only step quiescent material takes
+#pragma unroll 1
+  for (int it = 1; it < 16 && delta >= 3e-4f; ++it) {
+    det = cofactor3(X, Cf);
+    delta = polar_newton_step(X, Cf, det);
   }
   return X;
 }
