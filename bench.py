@@ -29,7 +29,11 @@ P_PER_GPU = 1 << 26
 BYTES_PER_PARTICLE = 252   # P2G read 100 + G2P read 52 + G2P write 100
 BYTES_PER_NODE = 80        # zero 16 + P2G write-back 16 + grid update 16+16 + G2P read 16
 # per-kernel algorithmic bytes (DESIGN.md "Kernels"): (bytes per particle, bytes per node)
-KERNEL_BYTES = {"reset": (0, 16), "p2g": (100, 16), "grid": (0, 32), "g2p": (152, 16)}
+# g2p2g = G2P of one substep + P2G of the next in one kernel: it does the work of both, so its
+# algorithmic bytes are the sum (252 B/particle); what it really has to move is
+# 152 B/particle + 32 B/node because the P2G inputs never leave the registers (reported beside it)
+KERNEL_BYTES = {"reset": (0, 16), "p2g": (100, 16), "grid": (0, 32), "g2p": (152, 16), "g2p2g": (252, 32)}
+FUSED_MIN_BYTES = (152, 32)
 E2E_SUBSTEPS_PER_SYNC = 20  # the reference main loop calls syncDevice every 20 advances (src/main.cu:99)
 
 
@@ -38,6 +42,20 @@ def peaks():
     if os.path.exists(p):
         return json.load(open(p))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(kernel, particles, nodes):
+    """dram bytes read + written per launch of `kernel` from the committed ncu --set full capture of
+    this workload (profiles/ncu_traffic.json, written by tools/ncu_summary.py); None if the capture
+    was taken at another size."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        rec = json.load(open(p))[kernel]
+        if rec["particles"] == particles and rec["nodes"] == nodes:
+            return rec["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    return None
 
 
 def workload(gpus):
@@ -160,6 +178,7 @@ def main():
     ap.add_argument("--particles", type=int, default=P_PER_GPU, help="particles per GPU (default 2^26)")
     ap.add_argument("--g2p", default="tile", choices=["tile", "direct"], help="G2P kernel (MpmParams.g2p_mode)")
     ap.add_argument("--p2g", default="runs", choices=["runs", "direct"], help="P2G kernel (MpmParams.p2g_mode)")
+    ap.add_argument("--fuse", default="off", choices=["g2p2g", "off"], help="substep pipeline (MpmParams.fuse_mode)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -200,7 +219,8 @@ def main():
     sim = mpm_b200.Sim(N, dt, mats, model=mpm_b200.FIXED_COROTATED, svd_mode=svd_mode, sort_every=args.sort_every,
                        x_begin=xb, x_end=xe, device=local_rank, capacity=cap,
                        p2g_mode=mpm_b200.P2G_RUNS if args.p2g == "runs" else mpm_b200.P2G_DIRECT,
-                       g2p_mode=mpm_b200.G2P_TILE if args.g2p == "tile" else mpm_b200.G2P_DIRECT)
+                       g2p_mode=mpm_b200.G2P_TILE if args.g2p == "tile" else mpm_b200.G2P_DIRECT,
+                       fuse_mode=mpm_b200.FUSE_G2P2G if args.fuse == "g2p2g" else mpm_b200.FUSE_OFF)
     if world > 1:
         from mpm_b200 import slabs as _slabs
 
@@ -249,14 +269,20 @@ def main():
     st = sim.stage_times()
     barrier()
     peak, peak_src = peaks()
-    substep_keys = ("reset", "p2g", "grid", "g2p")
+    substep_keys = ("reset", "p2g", "grid", "g2p", "g2p2g")
     dom = max(substep_keys, key=lambda s: st[s])
     bp, bn = KERNEL_BYTES[dom]
     dom_ms = st[dom] / n_prof
     achieved = (bp * P_local + bn * G_local) / (dom_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel_ms": dom_ms,
+                "traffic": ncu_traffic(dom, P_local, G_local), "peak_source": peak_src, "kernel_ms": dom_ms,
                 "algorithmic_bytes_per_launch": bp * P_local + bn * G_local}
+    if dom == "g2p2g":
+        mb = FUSED_MIN_BYTES[0] * P_local + FUSED_MIN_BYTES[1] * G_local
+        roofline["fused_min_bytes_per_launch"] = mb
+        roofline["achieved_on_fused_min_bytes"] = mb / (dom_ms * 1e-3) / 1e9
+        roofline["note"] = ("achieved = SURVEY 8(d) bytes of the two stages the kernel replaces (252 B/particle + 32 B/node) / time; "
+                            "the fused kernel itself must move only 152 B/particle + 32 B/node")
     sub_ach = (BYTES_PER_PARTICLE * P_all + BYTES_PER_NODE * G_all) / (ms_per_step * 1e-3) / 1e9 / world
     substep_roofline = {"achieved_per_gpu": sub_ach, "peak": peak, "unit": "GB/s", "frac": sub_ach / peak,
                         "bytes": "252*P + 80*G per substep (BASELINE.md)"}
@@ -297,7 +323,7 @@ def main():
             "config": {"workload": f"synthetic dense block N={N}, {int(P_all)} particles, fixed-corotated (BASELINE.json configs[3]"
                                    + (")" if world == 1 else f" scaled weakly to {world} GPUs: 2^26 particles and ~2^24 nodes per GPU)"),
                        "N": N, "particles": int(P_all), "grid_nodes": int(G_all), "dt": dt, "model": "fixed_corotated",
-                       "svd_mode": args.svd, "sort_every": args.sort_every, "p2g": args.p2g, "g2p": args.g2p, "slabs": slabs if world > 1 else None,
+                       "svd_mode": args.svd, "sort_every": args.sort_every, "p2g": args.p2g, "g2p": args.g2p, "fuse": args.fuse, "slabs": slabs if world > 1 else None,
                        "l2": "inputs (6.7 GB particles + 268 MB grid per GPU) are far larger than the 126 MB L2; no flush"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "substep_roofline": substep_roofline, "stage_ms": stage_ms,

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define MPM_B200_ABI_VERSION 2
+#define MPM_B200_ABI_VERSION 3
 
 /* which MaterialModel alias the kernels are instantiated for (reference include/mpm.cuh:25) */
 enum { MPM_MODEL_SNOW = 0, MPM_MODEL_FIXED_COROTATED = 1 };
@@ -37,9 +37,16 @@ enum { MPM_P2G_RUNS = 0, MPM_P2G_DIRECT = 1 };
 /* G2P kernel: TILE stages the grid block and the particle streams of each CTA in shared memory
  * with bulk async copies (default); DIRECT gathers the 27 nodes per particle from global memory */
 enum { MPM_G2P_TILE = 0, MPM_G2P_DIRECT = 1 };
+/* substep pipeline: OFF (default) runs reset -> P2G -> grid update -> G2P as separate kernels, as the
+ * reference does.  G2P2G runs G2P of substep s and P2G of substep s+1 as ONE warp-specialised kernel
+ * over two alternating grids, so the particle state written by G2P is never read back from HBM
+ * (needs P2G_RUNS + G2P_TILE, else the separate kernels run).  Same arithmetic per particle either
+ * way.  Measured slower than the separate kernels so far, hence not the default.
+ * In G2P2G mode the internal grid holds the NEXT substep's velocities after mpm_advance. */
+enum { MPM_FUSE_OFF = 0, MPM_FUSE_G2P2G = 1 };
 /* stage indices for mpm_get_stage_times */
 enum { MPM_STAGE_SORT = 0, MPM_STAGE_RESET = 1, MPM_STAGE_P2G = 2, MPM_STAGE_GRID = 3, MPM_STAGE_G2P = 4,
-       MPM_STAGE_EXCHANGE = 5, MPM_STAGE_COUNT = 6 };
+       MPM_STAGE_EXCHANGE = 5, MPM_STAGE_G2P2G = 6, MPM_STAGE_COUNT = 7 };
 
 /* replaces the reference's 104-byte particle record at the boundary */
 typedef struct MpmParticle {
@@ -78,7 +85,7 @@ typedef struct MpmParams {
   uint32_t ghost;       /* slab handles: extra ghost x-planes either side, i.e. how many cells a particle
                            may drift out of its slab between re-bins (0 = default: 1 for slabs) */
   uint32_t g2p_mode;    /* MPM_G2P_* */
-  uint32_t reserved_;   /* must be 0 */
+  uint32_t fuse_mode;   /* MPM_FUSE_* */
 } MpmParams;
 
 typedef struct MpmSim MpmSim;

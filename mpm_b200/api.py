@@ -10,7 +10,8 @@ SNOW, FIXED_COROTATED = 0, 1
 SVD_EXACT, SVD_FAST = 0, 1
 P2G_RUNS, P2G_DIRECT = 0, 1
 G2P_TILE, G2P_DIRECT = 0, 1
-STAGES = ("sort", "reset", "p2g", "grid", "g2p", "exchange")
+FUSE_OFF, FUSE_G2P2G = 0, 1
+STAGES = ("sort", "reset", "p2g", "grid", "g2p", "exchange", "g2p2g")
 
 # MpmParticle == the reference's MLS_APIC_Particle (104 bytes, matrices column-major)
 PARTICLE_DTYPE = np.dtype(
@@ -26,7 +27,7 @@ class MpmParams(ctypes.Structure):
                 ("svd_mode", ctypes.c_uint32), ("sort_every", ctypes.c_uint32), ("x_begin", ctypes.c_uint32),
                 ("x_end", ctypes.c_uint32), ("device", ctypes.c_int32), ("capacity", ctypes.c_uint64),
                 ("p2g_mode", ctypes.c_uint32), ("ghost", ctypes.c_uint32), ("g2p_mode", ctypes.c_uint32),
-                ("reserved_", ctypes.c_uint32)]
+                ("fuse_mode", ctypes.c_uint32)]
 
 
 class MpmError(RuntimeError):
@@ -103,10 +104,10 @@ class Sim:
     """One handle = one device.  Mirrors the device half of the reference's Simulation class."""
 
     def __init__(self, N, dt, materials, model=SNOW, svd_mode=SVD_EXACT, sort_every=0, x_begin=0, x_end=0,
-                 device=-1, capacity=0, p2g_mode=P2G_RUNS, ghost=0, g2p_mode=G2P_TILE):
+                 device=-1, capacity=0, p2g_mode=P2G_RUNS, ghost=0, g2p_mode=G2P_TILE, fuse_mode=FUSE_OFF):
         self._h = _vp()
         mats = np.ascontiguousarray(materials, np.float32).reshape(-1, 7)
-        self.params = MpmParams(dt, N, model, svd_mode, sort_every, x_begin, x_end, device, capacity, p2g_mode, ghost, g2p_mode, 0)
+        self.params = MpmParams(dt, N, model, svd_mode, sort_every, x_begin, x_end, device, capacity, p2g_mode, ghost, g2p_mode, fuse_mode)
         rc = lib().mpm_create(ctypes.byref(self.params), _ptr(mats), mats.shape[0], ctypes.byref(self._h))
         if rc:
             raise MpmError(lib().mpm_last_error(None).decode())

@@ -16,6 +16,7 @@
 #include "comm.cuh"
 #include "kernels.cuh"
 #include "g2p_tile.cuh"
+#include "g2p2g.cuh"
 #include "p2g_sched.cuh"
 #include "sort.cuh"
 
@@ -42,6 +43,12 @@ struct MpmSim {
   // grid: nxl * N * N float4
   float4* grid = nullptr;
   size_t grid_nodes = 0;
+  // fused mode (g2p2g.cuh): second grid, the two swap roles every substep.  grid_ready = `grid`
+  // already holds the updated velocities of the NEXT substep (scattered by the previous fused
+  // kernel from the particles' current state); any change to the particles or the grid clears it.
+  float4* grid_b = nullptr;
+  bool fused = false;
+  bool grid_ready = false;
 
   MpmMaterial* mats = nullptr;
   MpmMaterial mat0{};  // host copy of material 0: single-material handles pass it as a kernel parameter
@@ -75,6 +82,7 @@ struct MpmSim {
   // TMA descriptors: grid as [nxl][N][N][4 floats] with a 5 x 5 x LT box; particle streams of
   // each SoA buffer as [NSTREAM][stride] with kTile-column boxes of 12 / 13 / 25 rows
   CUtensorMap tm_grid[2];         // kLtSmall, kLtLarge
+  CUtensorMap tm_grid_b[2];       // the same over grid_b (fused mode)
   CUtensorMap tm_streams[2][3];   // [soa buffer][12, 13, 25 rows]
 
   MpmParticle* aos_stage = nullptr;  // device AoS staging for upload/download
@@ -146,7 +154,7 @@ int make_stream_maps(MpmSim* sim, int buf) {
   return 0;
 }
 
-int make_grid_maps(MpmSim* sim) {
+int make_grid_maps(MpmSim* sim, float4* grid, CUtensorMap* out) {
   EncodeTiledFn enc = encode_tiled();
   if (!enc) return fail(sim, "cuTensorMapEncodeTiled is not available from this driver");
   const cuuint64_t N = (cuuint64_t)sim->k.N;
@@ -156,7 +164,7 @@ int make_grid_maps(MpmSim* sim) {
     const cuuint64_t strides[3] = {16, 16 * N, 16 * N * N};
     const cuuint32_t box[4] = {4, (cuuint32_t)lts[i], 5, 5};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
-    const CUresult rc = enc(&sim->tm_grid[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, sim->grid, dims, strides, box, estr,
+    const CUresult rc = enc(&out[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, grid, dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc != CUDA_SUCCESS) return fail(sim, "cuTensorMapEncodeTiled(grid) failed: %d", (int)rc);
@@ -295,9 +303,9 @@ int do_sort(MpmSim* sim) {
   return 0;
 }
 
-int do_reset(MpmSim* sim) {
+int do_reset(MpmSim* sim, float4* grid = nullptr) {
   StageTimer tm(sim, MPM_STAGE_RESET);
-  CK(cudaMemsetAsync(sim->grid, 0, sizeof(float4) * sim->grid_nodes, sim->stream));
+  CK(cudaMemsetAsync(grid ? grid : sim->grid, 0, sizeof(float4) * sim->grid_nodes, sim->stream));
   return 0;
 }
 
@@ -396,6 +404,45 @@ int do_g2p(MpmSim* sim) {
   return 0;
 }
 
+template <int MODEL, class O, bool EXACT>
+void launch_g2p2g(MpmSim* sim) {
+  const size_t smem = FusedLayout<MODEL>::bytes();
+  const bool one = sim->n_mats == 1;
+  auto kern = one ? g2p2g_kernel<MODEL, O, EXACT, true> : g2p2g_kernel<MODEL, O, EXACT, false>;
+  static int per_sm[2] = {0, 0};  // per instantiation
+  if (!per_sm[one]) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[one], kern, kFusedThreads, smem);
+    per_sm[one] = std::max(per_sm[one], 1);
+  }
+  const size_t max_tiles = sim->count / kTileMax + sim->n_rows + 1;
+  const unsigned ctas = (unsigned)std::min<size_t>(max_tiles, (size_t)sim->n_sms * per_sm[one]);
+  kern<<<ctas, kFusedThreads, smem, sim->stream>>>(sim->soa[sim->cur], sim->mats, sim->mat0, sim->grid, sim->grid_b, sim->k, sim->tiles,
+                                                 sim->d_n_tiles, sim->tm_streams[sim->cur][MODEL == MPM_MODEL_SNOW ? 1 : 0]);
+}
+
+// G2P of this substep from sim->grid + P2G of the next substep into sim->grid_b (zeroed by the caller)
+int do_g2p2g(MpmSim* sim) {
+  StageTimer tm(sim, MPM_STAGE_G2P2G);
+  if (sim->count == 0) return 0;
+  const bool exact = sim->par.svd_mode == MPM_SVD_EXACT;
+  if (sim->par.model == MPM_MODEL_SNOW) {
+    if (exact) launch_g2p2g<MPM_MODEL_SNOW, ExactOps, true>(sim); else launch_g2p2g<MPM_MODEL_SNOW, FastOps, false>(sim);
+  } else {
+    if (exact) launch_g2p2g<MPM_MODEL_FIXED_COROTATED, ExactOps, true>(sim); else launch_g2p2g<MPM_MODEL_FIXED_COROTATED, FastOps, false>(sim);
+  }
+  sim->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int do_exchange(MpmSim* sim) {
+  if (!sim->comm.active()) return 0;
+  StageTimer tm(sim, MPM_STAGE_EXCHANGE);
+  if (sim->comm.exchange_halo(sim->grid, sim->k, sim->stream, &sim->launches)) return fail(sim, "halo exchange failed: %s", sim->comm.error());
+  return 0;
+}
+
 int bits_for(size_t n) {
   int b = 1;
   while (((size_t)1 << b) < n) ++b;
@@ -428,8 +475,8 @@ int mpm_create(const MpmParams* params, const MpmMaterial* materials, int n_mate
   if (params->N < 4) return fail(nullptr, "mpm_create: N must be >= 4");
   if (n_materials < 1 || n_materials > 256 || !materials) return fail(nullptr, "mpm_create: need 1..256 materials");
   if (params->model > MPM_MODEL_FIXED_COROTATED || params->svd_mode > MPM_SVD_FAST || params->p2g_mode > MPM_P2G_DIRECT ||
-      params->g2p_mode > MPM_G2P_DIRECT || params->reserved_ != 0)
-    return fail(nullptr, "mpm_create: bad model / svd_mode / p2g_mode / g2p_mode");
+      params->g2p_mode > MPM_G2P_DIRECT || params->fuse_mode > MPM_FUSE_G2P2G)
+    return fail(nullptr, "mpm_create: bad model / svd_mode / p2g_mode / g2p_mode / fuse_mode");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -488,6 +535,10 @@ int mpm_create(const MpmParams* params, const MpmMaterial* materials, int n_mate
   CKC(cudaEventCreate(&sim->ev[1]));
   CKC(cudaMalloc(&sim->grid, sizeof(float4) * sim->grid_nodes));
   CKC(cudaMemsetAsync(sim->grid, 0, sizeof(float4) * sim->grid_nodes, sim->stream));
+  // the fused kernel is built from the run-based P2G and the tile-based G2P
+  sim->fused = params->fuse_mode == MPM_FUSE_G2P2G && params->p2g_mode == MPM_P2G_RUNS && params->g2p_mode == MPM_G2P_TILE &&
+               N + kKeyBias <= 1023;
+  if (sim->fused) CKC(cudaMalloc(&sim->grid_b, sizeof(float4) * sim->grid_nodes));
   sim->n_mats = n_materials;
   sim->mat0 = materials[0];
   CKC(cudaMalloc(&sim->mats, sizeof(MpmMaterial) * n_materials));
@@ -497,7 +548,7 @@ int mpm_create(const MpmParams* params, const MpmMaterial* materials, int n_mate
   CKC(cudaMalloc(&sim->tile_base, sizeof(uint32_t) * ((size_t)sim->n_rows + 1)));
   CKC(cudaMalloc(&sim->d_n_tiles, sizeof(uint32_t)));
   CKC(cudaMemsetAsync(sim->d_n_tiles, 0, sizeof(uint32_t), sim->stream));
-  if (make_grid_maps(sim)) {
+  if (make_grid_maps(sim, sim->grid, sim->tm_grid) || (sim->fused && make_grid_maps(sim, sim->grid_b, sim->tm_grid_b))) {
     g_create_error = sim->err;
     mpm_destroy(sim);
     return 1;
@@ -530,6 +581,7 @@ void mpm_destroy(MpmSim* sim) {
   cudaFree(sim->table);
   cudaFree(sim->scan_sums);
   cudaFree(sim->grid);
+  cudaFree(sim->grid_b);
   cudaFree(sim->mats);
   cudaFree(sim->aos_stage);
   cudaFree(sim->d_counter);
@@ -556,6 +608,7 @@ static int upload_impl(MpmSim* sim, const MpmParticle* particles, size_t count, 
   sim->count = count;
   sim->first_id = 0;
   sim->cur = 0;
+  sim->grid_ready = false;
   if (count) {
     CK(cudaMemcpyAsync(sim->aos_stage, particles, sizeof(MpmParticle) * count, cudaMemcpyHostToDevice, sim->stream));
     aos_to_soa_kernel<<<blocks_for(count, 256), 256, 0, sim->stream>>>(sim->aos_stage, sim->soa[0], count, 0);
@@ -616,6 +669,7 @@ int mpm_generate_dense_block(MpmSim* sim, uint64_t first_id, uint64_t count, uin
     return fail(sim, "mpm_generate_dense_block: slab handles need MpmParams.capacity");
   }
   sim->cur = 0;
+  sim->grid_ready = false;
   sim->first_id = (uint32_t)first_id;
   CK(cudaMemsetAsync(sim->d_counter, 0, sizeof(unsigned long long), sim->stream));
   if (count) {
@@ -644,10 +698,12 @@ uint64_t mpm_kernel_launches(const MpmSim* sim) { return sim ? sim->launches : 0
 void* mpm_stream(MpmSim* sim) { return sim ? (void*)sim->stream : nullptr; }
 
 int mpm_stage_sort(MpmSim* sim) { if (!sim) return 1; CK(cudaSetDevice(sim->device)); return do_sort(sim); }
-int mpm_stage_reset_grid(MpmSim* sim) { if (!sim) return 1; CK(cudaSetDevice(sim->device)); return do_reset(sim); }
-int mpm_stage_p2g(MpmSim* sim) { if (!sim) return 1; CK(cudaSetDevice(sim->device)); return do_p2g(sim); }
-int mpm_stage_grid_update(MpmSim* sim) { if (!sim) return 1; CK(cudaSetDevice(sim->device)); return do_grid(sim); }
-int mpm_stage_g2p(MpmSim* sim) { if (!sim) return 1; CK(cudaSetDevice(sim->device)); return do_g2p(sim); }
+// the single stages work on the primary grid with the separate kernels and leave the fused
+// pipeline's look-ahead grid invalid (mpm_advance rebuilds it)
+int mpm_stage_reset_grid(MpmSim* sim) { if (!sim) return 1; CK(cudaSetDevice(sim->device)); sim->grid_ready = false; return do_reset(sim); }
+int mpm_stage_p2g(MpmSim* sim) { if (!sim) return 1; CK(cudaSetDevice(sim->device)); sim->grid_ready = false; return do_p2g(sim); }
+int mpm_stage_grid_update(MpmSim* sim) { if (!sim) return 1; CK(cudaSetDevice(sim->device)); sim->grid_ready = false; return do_grid(sim); }
+int mpm_stage_g2p(MpmSim* sim) { if (!sim) return 1; CK(cudaSetDevice(sim->device)); sim->grid_ready = false; return do_g2p(sim); }
 
 int mpm_advance(MpmSim* sim, int n_substeps) {
   if (!sim) return 1;
@@ -656,14 +712,30 @@ int mpm_advance(MpmSim* sim, int n_substeps) {
     if (sim->par.sort_every && sim->steps_since_sort >= sim->par.sort_every) {
       if (int rc = do_sort(sim)) return rc;
     }
-    if (int rc = do_reset(sim)) return rc;
-    if (int rc = do_p2g(sim)) return rc;
-    if (sim->comm.active()) {
-      StageTimer tm(sim, MPM_STAGE_EXCHANGE);
-      if (int rc = sim->comm.exchange_halo(sim->grid, sim->k, sim->stream, &sim->launches)) return fail(sim, "halo exchange failed: %s", sim->comm.error());
+    if (sim->fused) {
+      // `grid` = velocities of this substep (built here on the first substep after the particles
+      // changed, otherwise left by the previous fused kernel); the fused kernel gathers from it
+      // and scatters the next substep into grid_b, which then becomes `grid`.
+      if (!sim->grid_ready) {
+        if (int rc = do_reset(sim)) return rc;
+        if (int rc = do_p2g(sim)) return rc;
+        if (int rc = do_exchange(sim)) return rc;
+        if (int rc = do_grid(sim)) return rc;
+      }
+      if (int rc = do_reset(sim, sim->grid_b)) return rc;
+      if (int rc = do_g2p2g(sim)) return rc;
+      std::swap(sim->grid, sim->grid_b);
+      for (int i = 0; i < 2; ++i) std::swap(sim->tm_grid[i], sim->tm_grid_b[i]);
+      if (int rc = do_exchange(sim)) return rc;
+      if (int rc = do_grid(sim)) return rc;
+      sim->grid_ready = true;
+    } else {
+      if (int rc = do_reset(sim)) return rc;
+      if (int rc = do_p2g(sim)) return rc;
+      if (int rc = do_exchange(sim)) return rc;
+      if (int rc = do_grid(sim)) return rc;
+      if (int rc = do_g2p(sim)) return rc;
     }
-    if (int rc = do_grid(sim)) return rc;
-    if (int rc = do_g2p(sim)) return rc;
     sim->t += (double)sim->par.dt;
     sim->substeps++;
     sim->steps_since_sort++;
@@ -690,6 +762,7 @@ int mpm_debug_upload_grid(MpmSim* sim, const float* vec4, size_t n_nodes) {
   if (!sim || !vec4) return 1;
   CK(cudaSetDevice(sim->device));
   if (n_nodes != sim->grid_nodes) return fail(sim, "grid has %zu nodes, caller passed %zu", sim->grid_nodes, n_nodes);
+  sim->grid_ready = false;
   CK(cudaMemcpyAsync(sim->grid, vec4, sizeof(float4) * n_nodes, cudaMemcpyHostToDevice, sim->stream));
   CK(cudaStreamSynchronize(sim->stream));
   return 0;
@@ -699,6 +772,7 @@ int mpm_debug_overwrite_particles_aos(MpmSim* sim, const MpmParticle* particles,
   CK(cudaSetDevice(sim->device));
   if (count != sim->count || !sim->whole_domain) return fail(sim, "overwrite needs the same particle count on a whole-domain handle");
   if (count == 0) return 0;
+  sim->grid_ready = false;
   if (int rc = ensure_stage(sim, count)) return rc;
   CK(cudaMemcpyAsync(sim->aos_stage, particles, sizeof(MpmParticle) * count, cudaMemcpyHostToDevice, sim->stream));
   aos_overwrite_kernel<<<blocks_for(count, 256), 256, 0, sim->stream>>>(sim->aos_stage, sim->soa[sim->cur], count, sim->first_id);

@@ -12,7 +12,7 @@
 //            its run into a histogram bin by length (one shared-memory integer atomic); after one
 //            barrier every warp scans the 32 bins in registers and the heads write the block's run
 //            list in order of DESCENDING LENGTH.
-//   phase 1  three threads per run, one per stencil x-slab (9 nodes, 36 accumulators in
+//   phase 1  three threads per run, one per stencil z-node (9 nodes, 36 accumulators in
 //            registers), taken from the sorted list: the 32 lanes of a warp get runs of (nearly)
 //            equal length, so the accumulation loop does not diverge — with runs in memory order
 //            a warp waits for its longest run and half the issue slots are lost
@@ -115,12 +115,145 @@ __device__ __forceinline__ void bspline_w(float f, float w[3]) {
   w[2] = w[0] + a1;
 }
 
+struct BlockBarrier {
+  __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+
+// phase R: warp-local runs of equal keys, listed block-wide in order of descending length.
+// Expects sm.hist zeroed and sm.pay / sm.key of this thread written; two barriers inside.
+// other_hist (optional): histogram of the other payload buffer of a double-buffered caller, zeroed
+// here between the two barriers (see g2p2g.cuh).  Returns the number of runs.
+template <class Bar>
+__device__ __forceinline__ int p2g_list_runs(P2gSmem& sm, uint32_t key, int tid, Bar bar, uint32_t* other_hist = nullptr) {
+  const int lane = tid & 31;
+  const uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
+  const bool head = (lane == 0) || (prev != key);
+  const uint32_t heads = __ballot_sync(0xffffffffu, head);
+  const uint32_t rest = (lane == 31) ? 0u : (heads >> (lane + 1));
+  const int len = rest ? __ffs(rest) : (32 - lane);  // meaningful for heads
+  const bool listed = head && key != kInvalidKey;     // skipped particles / the tail of the last block scatter nothing
+  uint32_t slot = 0;
+  if (listed) slot = atomicAdd(&sm.hist[32 - len], 1u);
+  bar();
+  uint32_t incl = sm.hist[lane];
+  if (other_hist && tid < 32) other_hist[tid] = 0;
+  const uint32_t cnt = incl;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  const int n_runs = (int)__shfl_sync(0xffffffffu, incl, 31);
+  const uint32_t bin_base = __shfl_sync(0xffffffffu, incl - cnt, listed ? (32 - len) : 0);
+  if (listed) sm.runs[bin_base + slot] = (uint16_t)(tid | ((len - 1) << 8));
+  bar();
+  return n_runs;
+}
+
+// phase 1: three threads per run, one per stencil z-node (the 9 (x, y) nodes of that z = 36
+// accumulators in registers).  The three lanes of a run then reduce into three CONSECUTIVE float4
+// nodes (z is the fastest grid index): 48 contiguous bytes per run and reduction instruction.  With
+// one thread per x-slab instead, every lane of a reduction hit its own 128-byte line, and the
+// reductions alone took a fifth of the L1 data-pipe wavefronts of the kernel
+// (profiles/r01_ncu_v4_fused_ws.txt).
+// (tid = index of the thread among the `nthreads` that share the tile's run list)
+__device__ __forceinline__ void p2g_scatter_runs(const P2gSmem& sm, int n_runs, int tid, float4* __restrict__ grid, const KParams& k,
+                                                 int nthreads = kP2gBlock) {
+  const long long NN = (long long)k.N * k.N;
+  const int gx_lo = max(0, k.x0), gx_hi = min(k.N, k.x0 + k.nxl);
+  for (int u = tid; u < 3 * n_runs; u += nthreads) {
+    const int r = u / 3, c = u - 3 * r;
+    const uint32_t run = sm.runs[r];
+    const int s0 = (int)(run & 255u), s1 = s0 + (int)(run >> 8) + 1;
+    const uint32_t rk = sm.key[s0];
+    float4 acc[3][3];  // [x node][y node]
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) acc[i][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // this thread's z weight as a + b (f - c)^2
+    const float fc = (float)c;
+    const float wc = 1.5f - 0.5f * fc, wa = (c == 1) ? 0.75f : 0.0f, wb = (c == 1) ? -1.0f : 0.5f;
+#if defined(MPM_P2G_EXP) && (MPM_P2G_EXP & 4)  // experiment: no accumulation
+    if (n_runs < 0)
+#endif
+#pragma unroll 1
+    for (int s = s0; s < s1; ++s) {
+      const float4 r0 = sm.pay[s][0], r1 = sm.pay[s][1], r2 = sm.pay[s][2], r3 = sm.pay[s][3];
+      const float dz = r0.z - wc;
+      const float wzc = fmaf(wb * dz, dz, wa);
+      float wx[3], wy[3];
+      bspline_w(r0.x, wx);
+      bspline_w(r0.y, wy);
+      const float mass = r0.w;
+      float q[3] = {fmaf(fc, r3.y, r1.x), fmaf(fc, r3.z, r1.y), fmaf(fc, r3.w, r1.z)};
+      const float cx[3] = {r1.w, r2.x, r2.y};
+      const float cy[3] = {r2.z, r2.w, r3.x};
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const float wi = wzc * wx[i];
+        float qj[3] = {q[0], q[1], q[2]};
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const float wt = wi * wy[j];
+          acc[i][j].x = fmaf(wt, qj[0], acc[i][j].x);
+          acc[i][j].y = fmaf(wt, qj[1], acc[i][j].y);
+          acc[i][j].z = fmaf(wt, qj[2], acc[i][j].z);
+          acc[i][j].w = fmaf(wt, mass, acc[i][j].w);
+          if (j < 2) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) qj[d] += cy[d];
+          }
+        }
+        if (i < 2) {
+#pragma unroll
+          for (int d = 0; d < 3; ++d) q[d] += cx[d];
+        }
+      }
+    }
+    // flush: one vector reduction per node of this z
+    const int bx = (int)(rk >> 20) - kKeyBias, by = (int)((rk >> 10) & 1023u) - kKeyBias, bz = (int)(rk & 1023u) - kKeyBias;
+    const int gz = bz + c;
+    if (gz < 0 || gz >= k.N) continue;
+#if defined(MPM_P2G_EXP) && (MPM_P2G_EXP & 2)  // experiment: no reductions
+    if (acc[0][0].x + acc[1][1].y + acc[2][2].z + acc[0][1].w + acc[0][2].x + acc[1][0].x + acc[1][2].x + acc[2][0].x + acc[2][1].x != 1.2345e30f) continue;
+#endif
+    float4* gp = grid + ((long long)(bx - k.x0) * NN + (long long)by * k.N + gz);
+    if (bx >= gx_lo && bx + 2 < gx_hi && (unsigned)by <= (unsigned)(k.N - 3)) {  // whole 3 x 3 patch inside
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        float4* row = gp + i * NN;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) atomicAdd(row + j * k.N, acc[i][j]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int gx = bx + i;
+        if (gx < gx_lo || gx >= gx_hi) continue;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const int gy = by + j;
+          if (gy < 0 || gy >= k.N) continue;
+          atomicAdd(gp + (i * NN + (long long)j * k.N), acc[i][j]);
+        }
+      }
+    }
+  }
+}
+
+template <class Bar>
+__device__ __forceinline__ void p2g_list_and_scatter_runs(P2gSmem& sm, uint32_t key, int tid, float4* __restrict__ grid, const KParams& k, Bar bar) {
+  const int n_runs = p2g_list_runs(sm, key, tid, bar);
+  p2g_scatter_runs(sm, n_runs, tid, grid, k);
+}
+
 template <int MODEL, class O, bool EXACT, bool ONE_MAT>
 __global__ void __launch_bounds__(kP2gBlock, MPM_P2G_MINBLK)
 p2g_sched_kernel(Soa p, size_t count, const MpmMaterial* __restrict__ mats, const MpmMaterial mat0, float4* __restrict__ grid,
                  KParams k) {
   __shared__ P2gSmem sm;
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tid = threadIdx.x;
   const size_t pi = (size_t)blockIdx.x * kP2gBlock + tid;
   if (tid < 32) sm.hist[tid] = 0;
   __syncthreads();
@@ -154,104 +287,7 @@ p2g_sched_kernel(Soa p, size_t count, const MpmMaterial* __restrict__ mats, cons
   }
   sm.key[tid] = key;
 
-  // ---------------- phase R: warp-local runs, block-wide list sorted by length ----------------
-  const uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
-  const bool head = (lane == 0) || (prev != key);
-  const uint32_t heads = __ballot_sync(0xffffffffu, head);
-  const uint32_t rest = (lane == 31) ? 0u : (heads >> (lane + 1));
-  const int len = rest ? __ffs(rest) : (32 - lane);  // meaningful for heads
-  const bool listed = head && key != kInvalidKey;     // skipped particles / the tail of the last block scatter nothing
-  uint32_t slot = 0;
-  if (listed) slot = atomicAdd(&sm.hist[32 - len], 1u);
-  __syncthreads();
-  uint32_t incl = sm.hist[lane];
-  const uint32_t cnt = incl;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += t;
-  }
-  const int n_runs = (int)__shfl_sync(0xffffffffu, incl, 31);
-  const uint32_t bin_base = __shfl_sync(0xffffffffu, incl - cnt, listed ? (32 - len) : 0);
-  if (listed) sm.runs[bin_base + slot] = (uint16_t)(tid | ((len - 1) << 8));
-  __syncthreads();
-
-  // ---------------- phase 1: 3 threads per run ----------------
-  const long long NN = (long long)k.N * k.N;
-  const int gx_lo = max(0, k.x0), gx_hi = min(k.N, k.x0 + k.nxl);
-  for (int u = tid; u < 3 * n_runs; u += kP2gBlock) {
-    const int r = u / 3, i = u - 3 * r;
-    const uint32_t run = sm.runs[r];
-    const int s0 = (int)(run & 255u), s1 = s0 + (int)(run >> 8) + 1;
-    const uint32_t rk = sm.key[s0];
-    float4 acc[3][3];
-#pragma unroll
-    for (int j = 0; j < 3; ++j)
-#pragma unroll
-      for (int kz = 0; kz < 3; ++kz) acc[j][kz] = make_float4(0.f, 0.f, 0.f, 0.f);
-    // this thread's x-slab weight as a + b (f - c)^2
-    const float fi = (float)i;
-    const float wc = 1.5f - 0.5f * fi, wa = (i == 1) ? 0.75f : 0.0f, wb = (i == 1) ? -1.0f : 0.5f;
-#pragma unroll 1
-    for (int s = s0; s < s1; ++s) {
-      const float4 r0 = sm.pay[s][0], r1 = sm.pay[s][1], r2 = sm.pay[s][2], r3 = sm.pay[s][3];
-      const float dxi = r0.x - wc;
-      const float wxi = fmaf(wb * dxi, dxi, wa);
-      float wy[3], wz[3];
-      bspline_w(r0.y, wy);
-      bspline_w(r0.z, wz);
-      const float mass = r0.w;
-      float q[3] = {fmaf(fi, r1.w, r1.x), fmaf(fi, r2.x, r1.y), fmaf(fi, r2.y, r1.z)};
-      const float cy[3] = {r2.z, r2.w, r3.x};
-      const float cz[3] = {r3.y, r3.z, r3.w};
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const float wij = wxi * wy[j];
-        float qk[3] = {q[0], q[1], q[2]};
-#pragma unroll
-        for (int kz = 0; kz < 3; ++kz) {
-          const float wt = wij * wz[kz];
-          acc[j][kz].x = fmaf(wt, qk[0], acc[j][kz].x);
-          acc[j][kz].y = fmaf(wt, qk[1], acc[j][kz].y);
-          acc[j][kz].z = fmaf(wt, qk[2], acc[j][kz].z);
-          acc[j][kz].w = fmaf(wt, mass, acc[j][kz].w);
-          if (kz < 2) {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) qk[c] += cz[c];
-          }
-        }
-        if (j < 2) {
-#pragma unroll
-          for (int c = 0; c < 3; ++c) q[c] += cy[c];
-        }
-      }
-    }
-    // flush: one vector reduction per node of this slab
-    const int bx = (int)(rk >> 20) - kKeyBias, by = (int)((rk >> 10) & 1023u) - kKeyBias, bz = (int)(rk & 1023u) - kKeyBias;
-    const int gx = bx + i;
-    if (gx < gx_lo || gx >= gx_hi) continue;
-    float4* gp = grid + ((long long)(gx - k.x0) * NN + (long long)by * k.N + bz);
-    if ((unsigned)by <= (unsigned)(k.N - 3) && (unsigned)bz <= (unsigned)(k.N - 3)) {  // whole 3 x 3 patch inside
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        float4* row = gp + j * k.N;
-#pragma unroll
-        for (int kz = 0; kz < 3; ++kz) atomicAdd(row + kz, acc[j][kz]);
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const int gy = by + j;
-        if (gy < 0 || gy >= k.N) continue;
-#pragma unroll
-        for (int kz = 0; kz < 3; ++kz) {
-          const int gz = bz + kz;
-          if (gz < 0 || gz >= k.N) continue;
-          atomicAdd(gp + (j * k.N + kz), acc[j][kz]);
-        }
-      }
-    }
-  }
+  p2g_list_and_scatter_runs(sm, key, tid, grid, k, BlockBarrier());
 }
 
 }  // namespace mpm

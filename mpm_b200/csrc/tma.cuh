@@ -32,6 +32,30 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+// whole-warp wait with ONE polling lane (32 lanes probing the same barrier only multiply the
+// traffic on the shared-memory pipe); sleep_ns > 0 backs off between probes.  Must be called by
+// all 32 lanes; the __syncwarp orders the other lanes' reads after lane 0's acquire.
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, unsigned sleep_ns = 0) {
+  if ((threadIdx.x & 31) == 0) {
+    while (!mbar_try_wait(bar, parity)) {
+      if (sleep_ns) __nanosleep(sleep_ns);
+    }
+  }
+  __syncwarp();
+}
 // global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
