@@ -107,6 +107,10 @@ int mpm_upload_particles_aos(MpmSim* sim, const MpmParticle* particles, size_t c
 /* slab handles (multi-GPU): same, with caller-chosen global particle ids; such handles return
  * particles in their current (cell-sorted) order, ids via mpm_debug_download_sort */
 int mpm_upload_particles_with_ids(MpmSim* sim, const MpmParticle* particles, const uint32_t* ids, size_t count);
+/* adds particles to the active set on the device (an object whose lifetime begins, include/mpm.cuh:36-40;
+ * the reference re-uploads everything from stale host copies, src/mpm.cu:298-314).  Their ids continue
+ * the upload order.  Needs room: set MpmParams.capacity to the total over all objects. */
+int mpm_append_particles_aos(MpmSim* sim, const MpmParticle* particles, size_t count);
 /* particlesToHost (src/mpm.cu:288-306): blocking; particles come back in upload order */
 int mpm_download_particles_aos(MpmSim* sim, MpmParticle* particles, size_t capacity, size_t* count);
 /* positions only (12 B/particle), upload order — what the reference's viewer cadence needs */

@@ -65,6 +65,7 @@ def lib():
         L.mpm_make_material.argtypes = [ctypes.c_double] * 7 + [_vp]
         L.mpm_create.argtypes = [ctypes.POINTER(MpmParams), _vp, ctypes.c_int, ctypes.POINTER(_vp)]
         L.mpm_upload_particles_aos.argtypes = [_vp, _vp, ctypes.c_size_t]
+        L.mpm_append_particles_aos.argtypes = [_vp, _vp, ctypes.c_size_t]
         L.mpm_upload_particles_with_ids.argtypes = [_vp, _vp, _vp, ctypes.c_size_t]
         L.mpm_download_particles_aos.argtypes = [_vp, _vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
         L.mpm_download_positions.argtypes = [_vp, _vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
@@ -133,6 +134,11 @@ class Sim:
     def upload(self, particles):
         assert particles.dtype == PARTICLE_DTYPE and particles.flags.c_contiguous
         self._ck(lib().mpm_upload_particles_aos(self._h, _ptr(particles), particles.shape[0]))
+
+    def append(self, particles):
+        """More particles into the active set (an object whose lifetime begins); ids continue."""
+        assert particles.dtype == PARTICLE_DTYPE and particles.flags.c_contiguous
+        self._ck(lib().mpm_append_particles_aos(self._h, _ptr(particles), particles.shape[0]))
 
     def overwrite(self, particles):
         """New particle data (upload order) into the existing slots, without re-binning."""

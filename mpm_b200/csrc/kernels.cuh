@@ -9,10 +9,12 @@ namespace mpm {
 constexpr int kParticleBlock = 128;
 
 // ---- particle <-> AoS conversion (boundary only, off the hot path) ---------------------------
-__global__ void aos_to_soa_kernel(const MpmParticle* __restrict__ aos, Soa p, size_t count, uint32_t first_id) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+// aos[0..count) -> slots [offset, offset + count), ids first_id + slot
+__global__ void aos_to_soa_kernel(const MpmParticle* __restrict__ aos, Soa p, size_t count, uint32_t first_id, size_t offset = 0) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
   const MpmParticle& q = aos[i];
+  i += offset;
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
     p.s(SX + a)[i] = q.x[a];

@@ -628,6 +628,25 @@ int mpm_upload_particles_with_ids(MpmSim* sim, const MpmParticle* particles, con
   return upload_impl(sim, particles, count, ids);
 }
 
+int mpm_append_particles_aos(MpmSim* sim, const MpmParticle* particles, size_t count) {
+  if (!sim || (!particles && count)) return fail(sim, "mpm_append_particles_aos: null argument");
+  CK(cudaSetDevice(sim->device));
+  if (!sim->whole_domain) return fail(sim, "mpm_append_particles_aos: not for slab handles");
+  if (count == 0) return 0;
+  if (sim->count == 0) return upload_impl(sim, particles, count, nullptr);
+  if (sim->count + count > sim->capacity)
+    return fail(sim, "mpm_append_particles_aos: %zu + %zu particles exceed the capacity %zu (set MpmParams.capacity)", sim->count, count, sim->capacity);
+  if (int rc = ensure_stage(sim, count)) return rc;
+  CK(cudaMemcpyAsync(sim->aos_stage, particles, sizeof(MpmParticle) * count, cudaMemcpyHostToDevice, sim->stream));
+  // ids continue the upload order, so a later download returns old particles first, then these
+  aos_to_soa_kernel<<<blocks_for(count, 256), 256, 0, sim->stream>>>(sim->aos_stage, sim->soa[sim->cur], count, sim->first_id, sim->count);
+  sim->launches++;
+  CK(cudaGetLastError());
+  sim->count += count;
+  sim->grid_ready = false;
+  return do_sort(sim);
+}
+
 int mpm_download_particles_aos(MpmSim* sim, MpmParticle* particles, size_t capacity, size_t* count) {
   if (!sim) return 1;
   CK(cudaSetDevice(sim->device));
