@@ -260,7 +260,8 @@ int build_tiles(MpmSim* sim) {
   return 0;
 }
 
-int do_sort(MpmSim* sim) {
+// partial: called between the grid update and G2P, permutes only what G2P reads (sort.cuh)
+int do_sort(MpmSim* sim, bool partial = false) {
   StageTimer tm(sim, MPM_STAGE_SORT);
   sim->steps_since_sort = 0;
   size_t n_dead = 0;
@@ -294,7 +295,8 @@ int do_sort(MpmSim* sim) {
   }
   sim->sorted_cur = in;
   Soa& dst = sim->soa[sim->cur ^ 1];
-  permute_kernel<<<blocks_for(n, 256), 256, 0, sim->stream>>>(src, dst, sim->vals[in], n);
+  if (partial) permute_kernel<true><<<blocks_for(n, 256), 256, 0, sim->stream>>>(src, dst, sim->vals[in], n, sim->k);
+  else permute_kernel<false><<<blocks_for(n, 256), 256, 0, sim->stream>>>(src, dst, sim->vals[in], n, sim->k);
   sim->launches++;
   sim->cur ^= 1;
   sim->count = n - n_dead;  // tombstones were sorted behind the live particles
@@ -728,8 +730,13 @@ int mpm_advance(MpmSim* sim, int n_substeps) {
   if (!sim) return 1;
   CK(cudaSetDevice(sim->device));
   for (int s = 0; s < n_substeps; ++s) {
+    bool rebin_late = false;
     if (sim->par.sort_every && sim->steps_since_sort >= sim->par.sort_every) {
-      if (int rc = do_sort(sim)) return rc;
+      // slab handles migrate particles at the re-bin (whole records), the fused pipeline has no gap
+      rebin_late = !sim->comm.active() && !sim->fused && sim->count > 0;
+      if (!rebin_late) {
+        if (int rc = do_sort(sim)) return rc;
+      }
     }
     if (sim->fused) {
       // `grid` = velocities of this substep (built here on the first substep after the particles
@@ -753,6 +760,11 @@ int mpm_advance(MpmSim* sim, int n_substeps) {
       if (int rc = do_p2g(sim)) return rc;
       if (int rc = do_exchange(sim)) return rc;
       if (int rc = do_grid(sim)) return rc;
+      // a due re-bin runs here when it can: G2P is about to overwrite v and C, so only x, F, Jp
+      // have to move (the keys come from the positions this substep started with)
+      if (rebin_late) {
+        if (int rc = do_sort(sim, true)) return rc;
+      }
       if (int rc = do_g2p(sim)) return rc;
     }
     sim->t += (double)sim->par.dt;

@@ -187,20 +187,38 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
 // histogram tiles must match the scatter's tiles: tile t = keys [t*kSortTile, (t+1)*kSortTile)
 static_assert(kSortTile == kSortWarps * kSortItems * 32, "tile layout");
 
-// SoA permute: dst[r] = src[perm[r]] for every stream (+ id, material)
-__global__ void __launch_bounds__(256) permute_kernel(Soa src, Soa dst, const uint32_t* __restrict__ perm, size_t count) {
+// SoA permute: dst[r] = src[perm[r]] for every stream (+ id, material).
+// PARTIAL: only what G2P reads (x, F, Jp = stream rows 0..12, + id, material) — for a re-bin placed
+// between the grid update and G2P, which overwrites v and C of every particle it processes.  The
+// particles G2P leaves untouched (whole stencil outside the domain, src/mpm.cu:128-132) keep all
+// their streams.  58 % of the full permute's bytes.
+template <bool PARTIAL>
+__global__ void __launch_bounds__(256) permute_kernel(Soa src, Soa dst, const uint32_t* __restrict__ perm, size_t count, KParams k) {
+  static_assert(SX == 0 && SF == 3 && SJ == 12 && SV == 13, "rows 0..12 = x, F, Jp");
+  constexpr int NROWS = PARTIAL ? SV : NSTREAM;
   const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= count) return;
   const uint32_t s = perm[r];
-  float t[NSTREAM];
+  float t[NROWS];
 #pragma unroll
-  for (int q = 0; q < NSTREAM; ++q) t[q] = src.s(q)[s];
+  for (int q = 0; q < NROWS; ++q) t[q] = src.s(q)[s];
   const uint32_t id = src.id[s];
   const uint8_t mt = src.mat[s];
 #pragma unroll
-  for (int q = 0; q < NSTREAM; ++q) dst.s(q)[r] = t[q];
+  for (int q = 0; q < NROWS; ++q) dst.s(q)[r] = t[q];
   dst.id[r] = id;
   dst.mat[r] = mt;
+  if (PARTIAL) {
+    bool untouched = false;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const int base = (int)(t[SX + a] * k.dx_inv - 0.5f);
+      untouched = untouched || (base + 3 < 0 || base >= k.N);
+    }
+    if (untouched) {
+      for (int q = NROWS; q < NSTREAM; ++q) dst.s(q)[r] = src.s(q)[s];
+    }
+  }
 }
 
 }  // namespace mpm
