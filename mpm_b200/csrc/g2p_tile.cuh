@@ -30,7 +30,12 @@
 
 namespace mpm {
 
-constexpr int kBoxRows = 25;  // 5 x 5 rows of the node box
+#ifndef MPM_G2P_BOXW
+#define MPM_G2P_BOXW 5  // node box of a tile: BOXW x BOXW rows (5 = one row of slack either side, 3 = exactly the stencil rows)
+#endif
+constexpr int kBoxW = MPM_G2P_BOXW;
+constexpr int kBoxSlack = (kBoxW - 3) / 2;
+constexpr int kBoxRows = kBoxW * kBoxW;
 #ifndef MPM_G2P_STAGES
 #define MPM_G2P_STAGES 3
 #endif
@@ -160,8 +165,8 @@ __device__ __forceinline__ void g2p_tile_compute(const Soa& p, const MpmMaterial
   // ---- nodes from the tile's TMA box: stencil = box rows (di..di+2, dj..dj+2), nodes t..t+2 ----
   {
     const int di = bxl - h.x0b, dj = base[1] - h.y0b, t = base[2] - h.z0b;
-    if (valid && (unsigned)di <= 2u && (unsigned)dj <= 2u && (unsigned)t <= (unsigned)(LT - 3)) {
-      g2p_gather27<false>(box + (di * 5 + dj) * LT + t, LT, 5 * LT, w, d, acc);
+    if (valid && (unsigned)di <= (unsigned)(kBoxW - 3) && (unsigned)dj <= (unsigned)(kBoxW - 3) && (unsigned)t <= (unsigned)(LT - 3)) {
+      g2p_gather27<false>(box + (di * kBoxW + dj) * LT + t, LT, kBoxW * LT, w, d, acc);
       gathered = true;
     }
   }
@@ -306,8 +311,8 @@ g2p_tile_kernel(Soa p, const MpmMaterial* __restrict__ mats, const float4* __res
         TileHeader h;
         h.z0b = (int)(d.kfirst - row * (uint32_t)k.N) - 1;
         h.x0b = (int)(row / (uint32_t)k.N);
-        h.y0b = (int)(row - (uint32_t)h.x0b * (uint32_t)k.N) - 1;
-        h.x0b -= 1;
+        h.y0b = (int)(row - (uint32_t)h.x0b * (uint32_t)k.N) - kBoxSlack;
+        h.x0b -= kBoxSlack;
         h.n = (int)d.n;
         h.start = d.start;
         h.off = (int)(d.start & 3u);

@@ -162,7 +162,7 @@ int make_grid_maps(MpmSim* sim, float4* grid, CUtensorMap* out) {
   for (int i = 0; i < 2; ++i) {
     const cuuint64_t dims[4] = {4, N, N, (cuuint64_t)sim->k.nxl};
     const cuuint64_t strides[3] = {16, 16 * N, 16 * N * N};
-    const cuuint32_t box[4] = {4, (cuuint32_t)lts[i], 5, 5};
+    const cuuint32_t box[4] = {4, (cuuint32_t)lts[i], (cuuint32_t)kBoxW, (cuuint32_t)kBoxW};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     const CUresult rc = enc(&out[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, grid, dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,

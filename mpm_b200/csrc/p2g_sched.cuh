@@ -25,9 +25,12 @@
 namespace mpm {
 
 #ifndef MPM_P2G_MINBLK
-#define MPM_P2G_MINBLK 3
+#define MPM_P2G_MINBLK 4
 #endif
-constexpr int kP2gBlock = 256;
+#ifndef MPM_P2G_BLOCK
+#define MPM_P2G_BLOCK 256
+#endif
+constexpr int kP2gBlock = MPM_P2G_BLOCK;
 constexpr uint32_t kInvalidKey = 0xffffffffu;
 constexpr int kKeyBias = 4;  // base node >= -3 for particles that are not skipped
 
@@ -164,7 +167,7 @@ __device__ __forceinline__ void p2g_scatter_runs(const P2gSmem& sm, int n_runs, 
   for (int u = tid; u < 3 * n_runs; u += nthreads) {
     const int r = u / 3, c = u - 3 * r;
     const uint32_t run = sm.runs[r];
-    const int s0 = (int)(run & 255u), s1 = s0 + (int)(run >> 8) + 1;
+    const int s0 = (int)(run & 255u), s1 = s0 + (int)(run >> 8) + 1;  // kP2gBlock <= 256
     const uint32_t rk = sm.key[s0];
     float4 acc[3][3];  // [x node][y node]
 #pragma unroll
