@@ -58,13 +58,15 @@ def ncu_traffic(kernel, particles, nodes):
     return None
 
 
-def workload(gpus):
-    """Cubic N and balanced slabs for `gpus` ranks, 2^26 particles each."""
+def workload(gpus, scaling="weak"):
+    """Cubic N and balanced slabs for `gpus` ranks: weak = 2^26 particles per rank on a grid that
+    grows with the rank count, strong = BASELINE.json configs[3] as is (N = 256, 2^26 particles in
+    total) cut into thinner slabs."""
     from mpm_b200 import slabs
 
     if gpus == 1:
         return 256, [(0, 256)]
-    N = int(round(256 * gpus ** (1.0 / 3.0) / 2) * 2)
+    N = 256 if scaling == "strong" else int(round(256 * gpus ** (1.0 / 3.0) / 2) * 2)
     return N, slabs.balanced_slabs(N, gpus, 0.1, 0.9)
 
 
@@ -179,6 +181,10 @@ def main():
     ap.add_argument("--g2p", default="tile", choices=["tile", "direct"], help="G2P kernel (MpmParams.g2p_mode)")
     ap.add_argument("--p2g", default="runs", choices=["runs", "direct"], help="P2G kernel (MpmParams.p2g_mode)")
     ap.add_argument("--fuse", default="off", choices=["g2p2g", "off"], help="substep pipeline (MpmParams.fuse_mode)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = 2^26 particles per GPU (default), strong = 2^26 particles in total at N = 256")
+    ap.add_argument("--model", default="fixed_corotated", choices=["fixed_corotated", "snow"],
+                    help="material model; snow = BASELINE.json configs[4] (plasticity via svd3 in G2P)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -208,15 +214,19 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    N, slabs = workload(world)
+    N, slabs = workload(world, args.scaling)
     xb, xe = slabs[rank]
-    P_total = args.particles * world
+    P_total = args.particles * (world if args.scaling == "weak" else 1)
     dt = 1e-4
     density = P_total / 0.512  # --particle-count: the block fills 0.8^3 of the unit cube
-    mats = mpm_b200.make_material(1.0 / density, 1000.0, 1.4e5, 0.2, 0.0, 0.0, 1e30)
+    snow = args.model == "snow"
+    if snow:  # scenes/snowman.toml material
+        mats = mpm_b200.make_material(1.0 / density, 700.0, 1.4e5, 0.2, 10.0, 0.975, 1.0075)
+    else:
+        mats = mpm_b200.make_material(1.0 / density, 1000.0, 1.4e5, 0.2, 0.0, 0.0, 1e30)
     svd_mode = mpm_b200.SVD_FAST if args.svd == "fast" else mpm_b200.SVD_EXACT
-    cap = int(args.particles * 1.15) if world > 1 else 0
-    sim = mpm_b200.Sim(N, dt, mats, model=mpm_b200.FIXED_COROTATED, svd_mode=svd_mode, sort_every=args.sort_every,
+    cap = int(P_total / world * 1.15) if world > 1 else 0
+    sim = mpm_b200.Sim(N, dt, mats, model=mpm_b200.SNOW if snow else mpm_b200.FIXED_COROTATED, svd_mode=svd_mode, sort_every=args.sort_every,
                        x_begin=xb, x_end=xe, device=local_rank, capacity=cap,
                        p2g_mode=mpm_b200.P2G_RUNS if args.p2g == "runs" else mpm_b200.P2G_DIRECT,
                        g2p_mode=mpm_b200.G2P_TILE if args.g2p == "tile" else mpm_b200.G2P_DIRECT,
@@ -319,10 +329,11 @@ def main():
         out = {
             "metric": "particle_steps_per_s", "value": value, "unit": "particle-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"synthetic dense block N={N}, {int(P_all)} particles, fixed-corotated (BASELINE.json configs[3]"
-                                   + (")" if world == 1 else f" scaled weakly to {world} GPUs: 2^26 particles and ~2^24 nodes per GPU)"),
-                       "N": N, "particles": int(P_all), "grid_nodes": int(G_all), "dt": dt, "model": "fixed_corotated",
+            "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"synthetic dense block N={N}, {int(P_all)} particles, {args.model} (BASELINE.json configs[{4 if snow else 3}]"
+                                   + (")" if world == 1 else (f" scaled weakly to {world} GPUs: 2^26 particles and ~2^24 nodes per GPU)" if args.scaling == "weak"
+                                                              else f" strong scaling: the same block cut into {world} slabs)")),
+                       "N": N, "particles": int(P_all), "grid_nodes": int(G_all), "dt": dt, "model": args.model,
                        "svd_mode": args.svd, "sort_every": args.sort_every, "p2g": args.p2g, "g2p": args.g2p, "fuse": args.fuse, "slabs": slabs if world > 1 else None,
                        "l2": "inputs (6.7 GB particles + 268 MB grid per GPU) are far larger than the 126 MB L2; no flush"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,

@@ -115,6 +115,11 @@ int mpm_append_particles_aos(MpmSim* sim, const MpmParticle* particles, size_t c
 int mpm_download_particles_aos(MpmSim* sim, MpmParticle* particles, size_t capacity, size_t* count);
 /* positions only (12 B/particle), upload order — what the reference's viewer cadence needs */
 int mpm_download_positions(MpmSim* sim, float* xyz, size_t capacity, size_t* count);
+/* the same without blocking: the copy is queued behind the substeps issued so far and overlaps the
+ * ones issued afterwards only if xyz is pinned host memory; read it after mpm_sync().  This is the
+ * reference's viewer cadence (src/main.cu:99-102) without stalling the substep pipeline.  The staging
+ * buffer is shared with the other transfers: one transfer in flight at a time. */
+int mpm_download_positions_async(MpmSim* sim, float* xyz, size_t capacity, size_t* count);
 /* synthetic dense block generated on the device: ids
  * [first_id, first_id+count), x = lo + (hi-lo)*u(hash(seed,id,axis)), v=0, F=I, C=0, Jp=1;
  * only particles whose base node lies in this handle's slab are kept */

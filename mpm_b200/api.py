@@ -69,6 +69,7 @@ def lib():
         L.mpm_upload_particles_with_ids.argtypes = [_vp, _vp, _vp, ctypes.c_size_t]
         L.mpm_download_particles_aos.argtypes = [_vp, _vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
         L.mpm_download_positions.argtypes = [_vp, _vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
+        L.mpm_download_positions_async.argtypes = [_vp, _vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
         L.mpm_generate_dense_block.argtypes = [_vp, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_float,
                                                ctypes.c_float, ctypes.c_uint8]
         L.mpm_advance.argtypes = [_vp, ctypes.c_int]
@@ -171,6 +172,12 @@ class Sim:
         cnt = ctypes.c_size_t()
         self._ck(lib().mpm_download_positions(self._h, _ptr(out), out.shape[0], ctypes.byref(cnt)))
         return out
+
+    def download_positions_async(self, out):
+        """Queues the positions read-back into `out` (float32 [count, 3], ideally pinned); valid after sync()."""
+        cnt = ctypes.c_size_t()
+        self._ck(lib().mpm_download_positions_async(self._h, _ptr(out), out.shape[0], ctypes.byref(cnt)))
+        return cnt.value
 
     def generate_dense_block(self, count, seed=1234, lo=0.1, hi=0.9, material=0, first_id=0):
         self._ck(lib().mpm_generate_dense_block(self._h, first_id, count, seed, lo, hi, material))

@@ -60,7 +60,7 @@ constexpr int kFusedStages = MPM_FUSED_STAGES;
 constexpr int kFusedPbuf = MPM_FUSED_PBUF;
 constexpr int kFusedNS = MPM_FUSED_NS;
 constexpr int kFusedThreads = kTile + 32 + 32 * kFusedNS;  // gather warps, producer warp, scatter warps
-static_assert(kTile == kP2gBlock, "one tile = one P2G block");
+static_assert(kTile == kP2gBlock || MPM_P2G_BLOCK != 256, "one tile = one P2G block");
 static_assert(kFusedPbuf >= 2 && (kFusedNS == 1 || kFusedNS == 2 || kFusedNS == 4 || kFusedNS == 8), "see above");
 
 struct ScatterBarrier {  // the scatter warps only
@@ -102,7 +102,7 @@ __device__ __forceinline__ int fused_list_runs(P2gSmem& sm, int ts, uint32_t* ne
 #pragma unroll
   for (int g = 0; g < NG; ++g) {
     const uint32_t bin_base = __shfl_sync(0xffffffffu, incl - cnt, listed[g] ? (32 - len[g]) : 0);
-    if (listed[g]) sm.runs[bin_base + slot[g]] = (uint16_t)(((w * NG + g) * 32 + lane) | ((len[g] - 1) << 8));
+    if (listed[g]) sm.runs[bin_base + slot[g]] = (uint16_t)(((w * NG + g) * 32 + lane) | ((len[g] - 1) << kRunPosBits));
   }
   bar();
   return n_runs;

@@ -664,7 +664,7 @@ int mpm_download_particles_aos(MpmSim* sim, MpmParticle* particles, size_t capac
   return 0;
 }
 
-int mpm_download_positions(MpmSim* sim, float* xyz, size_t capacity, size_t* count) {
+int mpm_download_positions_async(MpmSim* sim, float* xyz, size_t capacity, size_t* count) {
   if (!sim) return 1;
   CK(cudaSetDevice(sim->device));
   if (count) *count = sim->count;
@@ -676,6 +676,10 @@ int mpm_download_positions(MpmSim* sim, float* xyz, size_t capacity, size_t* cou
   sim->launches++;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(xyz, stage, sizeof(float) * 3 * sim->count, cudaMemcpyDeviceToHost, sim->stream));
+  return 0;
+}
+int mpm_download_positions(MpmSim* sim, float* xyz, size_t capacity, size_t* count) {
+  if (int rc = mpm_download_positions_async(sim, xyz, capacity, count)) return rc;
   CK(cudaStreamSynchronize(sim->stream));
   return 0;
 }

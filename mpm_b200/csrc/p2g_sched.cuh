@@ -27,10 +27,15 @@ namespace mpm {
 #ifndef MPM_P2G_MINBLK
 #define MPM_P2G_MINBLK 4
 #endif
+#ifndef MPM_P2G_CAP
+#define MPM_P2G_CAP 0  // 0 = runs as long as the warp allows
+#endif
 #ifndef MPM_P2G_BLOCK
 #define MPM_P2G_BLOCK 256
 #endif
 constexpr int kP2gBlock = MPM_P2G_BLOCK;
+constexpr int kRunPosBits = kP2gBlock > 256 ? 9 : 8;  // run list entry = first particle | (length - 1) << kRunPosBits
+static_assert(kP2gBlock <= 512, "run list entries are 16 bits");
 constexpr uint32_t kInvalidKey = 0xffffffffu;
 constexpr int kKeyBias = 4;  // base node >= -3 for particles that are not skipped
 
@@ -130,8 +135,15 @@ template <class Bar>
 __device__ __forceinline__ int p2g_list_runs(P2gSmem& sm, uint32_t key, int tid, Bar bar, uint32_t* other_hist = nullptr) {
   const int lane = tid & 31;
   const uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
-  const bool head = (lane == 0) || (prev != key);
-  const uint32_t heads = __ballot_sync(0xffffffffu, head);
+  bool head = (lane == 0) || (prev != key);
+  uint32_t heads = __ballot_sync(0xffffffffu, head);
+#if MPM_P2G_CAP
+  {  // long runs are cut into pieces of at most MPM_P2G_CAP particles: shorter dependent chains in phase 1
+    const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+    head = head || ((lane - start) % MPM_P2G_CAP == 0);
+    heads = __ballot_sync(0xffffffffu, head);
+  }
+#endif
   const uint32_t rest = (lane == 31) ? 0u : (heads >> (lane + 1));
   const int len = rest ? __ffs(rest) : (32 - lane);  // meaningful for heads
   const bool listed = head && key != kInvalidKey;     // skipped particles / the tail of the last block scatter nothing
@@ -148,7 +160,7 @@ __device__ __forceinline__ int p2g_list_runs(P2gSmem& sm, uint32_t key, int tid,
   }
   const int n_runs = (int)__shfl_sync(0xffffffffu, incl, 31);
   const uint32_t bin_base = __shfl_sync(0xffffffffu, incl - cnt, listed ? (32 - len) : 0);
-  if (listed) sm.runs[bin_base + slot] = (uint16_t)(tid | ((len - 1) << 8));
+  if (listed) sm.runs[bin_base + slot] = (uint16_t)(tid | ((len - 1) << kRunPosBits));
   bar();
   return n_runs;
 }
@@ -167,7 +179,7 @@ __device__ __forceinline__ void p2g_scatter_runs(const P2gSmem& sm, int n_runs, 
   for (int u = tid; u < 3 * n_runs; u += nthreads) {
     const int r = u / 3, c = u - 3 * r;
     const uint32_t run = sm.runs[r];
-    const int s0 = (int)(run & 255u), s1 = s0 + (int)(run >> 8) + 1;  // kP2gBlock <= 256
+    const int s0 = (int)(run & ((1u << kRunPosBits) - 1u)), s1 = s0 + (int)(run >> kRunPosBits) + 1;
     const uint32_t rk = sm.key[s0];
     float4 acc[3][3];  // [x node][y node]
 #pragma unroll

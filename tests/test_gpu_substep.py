@@ -231,6 +231,22 @@ def test_fused_pipeline_matches_separate_kernels(kind, sort_every):
     assert np.abs(a["v"].astype(np.float64) - ref["v"]).max() <= 1e-3 * np.abs(ref["v"]).max()
 
 
+def test_positions_readback_blocking_and_async():
+    """positions-only read-back (12 B/particle) in upload order, blocking and queued."""
+    N = 32
+    p, mats = scenes.two_spheres(N)
+    sim = _sim(N, mats, ol.SNOW, sort_every=2)
+    sim.upload(p)
+    sim.advance(3)
+    out = np.zeros((len(p), 3), np.float32)
+    assert sim.download_positions_async(out) == len(p)
+    sim.advance(2)          # queued behind the copy: must not disturb it
+    sim.sync()
+    ref, _ = ol.advance(p.copy(), mats, DT, N, ol.SNOW, 3)
+    assert np.abs(out.astype(np.float64) - ref["x"]).max() * N < 1e-4
+    assert np.array_equal(sim.download_positions(), sim.download()["x"])
+
+
 def test_free_fall_velocity():
     """Oracle-free invariant: before contact v_y(t) = -9.81 t (SURVEY.md 8(c) pin 6)."""
     N = 32
