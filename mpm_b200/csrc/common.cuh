@@ -102,9 +102,41 @@ __device__ __forceinline__ Mat3 compute_PF(const Mat3& F, float Jp, const MpmMat
   return PF;
 }
 
-// snow plasticity (reference MMSnow::endOfStepMutation, include/MaterialModel.cuh:95-114)
+// true when every singular value of F lies strictly inside (lo, hi) and det F > 0, i.e. when the
+// clamp of MMSnow::endOfStepMutation changes nothing: with C = F^T F, both C - lo^2 I and
+// hi^2 I - C are positive definite (Sylvester's criterion, three leading minors each).
+__device__ __forceinline__ bool pd3(float a11, float a12, float a13, float a22, float a23, float a33) {
+  const float m2 = a11 * a22 - a12 * a12;
+  const float det = a11 * (a22 * a33 - a23 * a23) - a12 * (a12 * a33 - a13 * a23) + a13 * (a12 * a23 - a13 * a22);
+  return a11 > 0.0f && m2 > 0.0f && det > 0.0f;
+}
+__device__ __forceinline__ bool snow_within_elastic_range(const Mat3& F, float lo, float hi) {
+  if (!(det3(F) > 0.0f)) return false;
+  float c[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = i; j < 3; ++j) c[i][j] = F.m[0][i] * F.m[0][j] + F.m[1][i] * F.m[1][j] + F.m[2][i] * F.m[2][j];
+  const float l2 = lo * lo;
+  if (!pd3(c[0][0] - l2, c[0][1], c[0][2], c[1][1] - l2, c[1][2], c[2][2] - l2)) return false;
+  if (hi > 1.0e15f) return true;  // "rubber": no upper clamp (hi^2 would overflow)
+  const float h2 = hi * hi;
+  return pd3(h2 - c[0][0], -c[0][1], -c[0][2], h2 - c[1][1], -c[1][2], h2 - c[2][2]);
+}
+
+// snow plasticity (reference MMSnow::endOfStepMutation, include/MaterialModel.cuh:95-114).
+// FAST mode skips the SVD for particles inside the elastic range: there the reference only
+// re-synthesises F = U S V^T and Jp * det F / det F from the SVD's own round-off (~1e-6), so
+// leaving F and Jp untouched is within the FAST tolerance (tests/test_gpu_substep.py); EXACT mode
+// always runs the full sequence, bit for bit.
 template <class O>
 __device__ __forceinline__ void snow_plasticity(Mat3& F, float& Jp, const MpmMaterial& m) {
+  if constexpr (!O::kExact) {
+    if (snow_within_elastic_range(F, m.plast_clamp_lower, m.plast_clamp_higher)) {
+      Jp = clampf(Jp, 0.6f, 20.0f);  // the outer clamp of the Jp update still applies
+      return;
+    }
+  }
   Mat3 U, V;
   float sig[3];
   svd3<O>(F, U, sig, V);
