@@ -736,8 +736,9 @@ int mpm_advance(MpmSim* sim, int n_substeps) {
   for (int s = 0; s < n_substeps; ++s) {
     bool rebin_late = false;
     if (sim->par.sort_every && sim->steps_since_sort >= sim->par.sort_every) {
-      // slab handles migrate particles at the re-bin (whole records), the fused pipeline has no gap
-      rebin_late = !sim->comm.active() && !sim->fused && sim->count > 0;
+      // (slab handles migrate whole particle records at the re-bin: v and C are still the previous
+      // substep's there, so leavers carry a complete state; the fused pipeline has no such gap)
+      rebin_late = !sim->fused;
       if (!rebin_late) {
         if (int rc = do_sort(sim)) return rc;
       }
