@@ -48,7 +48,10 @@ constexpr int kBoxRows = kBoxW * kBoxW;
 #define MPM_G2P_BOX (MPM_G2P_GATHER == 0)
 constexpr int kWarpBrickX = 4, kWarpBrickY = 4, kWarpBrickZ = 16;  // nodes; 4 KB of shared memory per warp
 constexpr int kG2pStages = MPM_G2P_STAGES;
-constexpr int kG2pThreads = kTile + 32;  // consumers + one producer warp
+#ifndef MPM_G2P_SELFFEED
+#define MPM_G2P_SELFFEED 1  // 1: no producer warp — the last warp to release a stage refills it (256 threads, 64 registers, 4 CTAs/SM)
+#endif
+constexpr int kG2pThreads = MPM_G2P_SELFFEED ? kTile : kTile + 32;  // consumers (+ one producer warp)
 
 struct TileHeader {  // written by the producer next to each stage
   int x0b, y0b, z0b;   // box origin in local grid coordinates (may be -1)
@@ -274,7 +277,7 @@ __device__ __forceinline__ void g2p_tile_compute(const Soa& p, const MpmMaterial
 
 // Persistent CTAs: tile `it` of this CTA = blockIdx.x + it * gridDim.x.
 template <int MODEL, class O, int LT>
-__global__ void __launch_bounds__(kG2pThreads, MPM_G2P_TILE_MINBLK)
+__global__ void __launch_bounds__(kG2pThreads, MPM_G2P_SELFFEED ? 4 : MPM_G2P_TILE_MINBLK)
 g2p_tile_kernel(Soa p, const MpmMaterial* __restrict__ mats, const float4* __restrict__ grid, KParams k,
                 const TileDesc* __restrict__ tiles, const uint32_t* __restrict__ n_tiles_ptr,
                 const __grid_constant__ CUtensorMap tm_grid, const __grid_constant__ CUtensorMap tm_streams) {
@@ -298,6 +301,38 @@ g2p_tile_kernel(Soa p, const MpmMaterial* __restrict__ mats, const float4* __res
   }
   __syncthreads();
 
+  // one TMA request: header + stream rows (+ node box) of tile t into stage s
+  auto issue = [&](uint32_t t, int s) {
+    const TileDesc d = tiles[t];
+    const uint32_t row = d.kfirst / (uint32_t)k.N;
+    TileHeader h;
+    h.z0b = (int)(d.kfirst - row * (uint32_t)k.N) - 1;
+    h.x0b = (int)(row / (uint32_t)k.N);
+    h.y0b = (int)(row - (uint32_t)h.x0b * (uint32_t)k.N) - kBoxSlack;
+    h.x0b -= kBoxSlack;
+    h.n = (int)d.n;
+    h.start = d.start;
+    h.off = (int)(d.start & 3u);
+    hdr[s] = h;
+    unsigned char* st = smem + s * kStage;
+    mbar_arrive_expect_tx(full + s, (uint32_t)kStage);
+    if (MPM_G2P_BOX) tma_load_4d(st, &tm_grid, 0, h.z0b, h.y0b, h.x0b, full + s);
+    tma_load_2d(st + L::box_bytes(LT), &tm_streams, (int)(d.start & ~3u), 0, full + s);
+  };
+#if MPM_G2P_SELFFEED
+  // No producer warp: thread 0 fills the ring once, afterwards the LAST warp to finish with a stage
+  // (a shared-memory counter tells it so) requests the tile that goes there next.  Nobody waits.
+  uint32_t* rel = reinterpret_cast<uint32_t*>(empty);  // the "empty" barriers are unused: one counter per stage
+  if (tid == 0) {
+    tma_prefetch_desc(&tm_streams);
+    for (int s = 0; s < kG2pStages; ++s) {
+      rel[2 * s] = 0;
+      const uint32_t t = blockIdx.x + (uint32_t)s * gridDim.x;
+      if (t < n_tiles) issue(t, s);
+    }
+  }
+  __syncthreads();
+#else
   if (tid >= kTile) {  // ---- producer warp: one elected lane feeds the ring ----
     if (tid == kTile) {
       tma_prefetch_desc(&tm_grid);
@@ -306,25 +341,12 @@ g2p_tile_kernel(Soa p, const MpmMaterial* __restrict__ mats, const float4* __res
       for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
         const int s = it % kG2pStages;
         if (it >= kG2pStages) mbar_wait(empty + s, (uint32_t)(((it / kG2pStages) - 1) & 1));
-        const TileDesc d = tiles[t];
-        const uint32_t row = d.kfirst / (uint32_t)k.N;
-        TileHeader h;
-        h.z0b = (int)(d.kfirst - row * (uint32_t)k.N) - 1;
-        h.x0b = (int)(row / (uint32_t)k.N);
-        h.y0b = (int)(row - (uint32_t)h.x0b * (uint32_t)k.N) - kBoxSlack;
-        h.x0b -= kBoxSlack;
-        h.n = (int)d.n;
-        h.start = d.start;
-        h.off = (int)(d.start & 3u);
-        hdr[s] = h;
-        unsigned char* st = smem + s * kStage;
-        mbar_arrive_expect_tx(full + s, (uint32_t)kStage);
-        if (MPM_G2P_BOX) tma_load_4d(st, &tm_grid, 0, h.z0b, h.y0b, h.x0b, full + s);
-        tma_load_2d(st + L::box_bytes(LT), &tm_streams, (int)(d.start & ~3u), 0, full + s);
+        issue(t, s);
       }
     }
     return;
   }
+#endif
   // ---- consumer warps ----
   int it = 0;
   for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
@@ -335,7 +357,22 @@ g2p_tile_kernel(Soa p, const MpmMaterial* __restrict__ mats, const float4* __res
                                    bricks + (tid >> 5) * (kWarpBrickX * kWarpBrickY * kWarpBrickZ),
                                    reinterpret_cast<const float*>(st + L::box_bytes(LT)), tid);
     __syncwarp();  // stage s and the warp's brick are free again
+#if MPM_G2P_SELFFEED
+    if ((tid & 31) == 0) {
+      __threadfence_block();
+      if (atomicAdd(&rel[2 * s], 1u) == kTile / 32 - 1) {
+        rel[2 * s] = 0;
+        __threadfence_block();
+        const uint32_t tn = t + (uint32_t)kG2pStages * gridDim.x;
+        if (tn < n_tiles) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the warps' reads of the stage before the copy engine's writes
+          issue(tn, s);
+        }
+      }
+    }
+#else
     if ((tid & 31) == 0) mbar_arrive(empty + s);
+#endif
   }
 }
 
