@@ -84,7 +84,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -93,11 +93,14 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.monotonic(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Samples taken inside [t0, t1] (host monotonic clock around the timed region); the sampler is
+        started before the warm-up so that nvidia-smi is already streaming when the region begins."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -105,7 +108,12 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        inside = [r for (t, r) in self.rows if t0 is None or (t0 <= t <= t1 + 0.03)]
+        window = "timed region"
+        if not inside:  # a very short region can fall between two samples: use the ones around it
+            inside = [r for (t, r) in self.rows if t0 is None or (t0 - 0.5 <= t <= t1 + 0.5)]
+            window = "timed region +- 0.5 s (none fell inside)"
+        for r in inside:
             try:
                 sm.append(float(r[1]))
                 smax.append(float(r[2]))
@@ -115,7 +123,7 @@ class ClockSampler:
             except Exception:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def run_reference(args):
@@ -241,13 +249,14 @@ def main():
     G_local = sim.grid_nodes
 
     stream = torch.cuda.ExternalStream(sim.stream)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         sim.advance(1)
     sim.sync()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    t_region0 = time.monotonic()
     launches0 = sim.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -257,7 +266,7 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1)
     launches = sim.launches - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_region0, time.monotonic()) if rank == 0 else None
     t = torch.tensor([ms, float(P_local), float(G_local)], dtype=torch.float64, device="cuda")
     if world > 1:
         tmax = t.clone()

@@ -316,9 +316,11 @@ void launch_p2g_sched(MpmSim* sim) {
   const size_t n = sim->count;
   const unsigned nbr = blocks_for(n, kP2gBlock);
   if (sim->n_mats == 1)
-    p2g_sched_kernel<MODEL, O, EXACT, true><<<nbr, kP2gBlock, 0, sim->stream>>>(sim->soa[sim->cur], n, sim->mats, sim->mat0, sim->grid, sim->k);
+    p2g_sched_kernel<MODEL, O, EXACT, true><<<nbr, kP2gBlock, 0, sim->stream>>>(sim->soa[sim->cur], n, sim->mats, sim->mat0, sim->grid, sim->k,
+                                                                                sim->tm_streams[sim->cur][2]);
   else
-    p2g_sched_kernel<MODEL, O, EXACT, false><<<nbr, kP2gBlock, 0, sim->stream>>>(sim->soa[sim->cur], n, sim->mats, sim->mat0, sim->grid, sim->k);
+    p2g_sched_kernel<MODEL, O, EXACT, false><<<nbr, kP2gBlock, 0, sim->stream>>>(sim->soa[sim->cur], n, sim->mats, sim->mat0, sim->grid, sim->k,
+                                                                                 sim->tm_streams[sim->cur][2]);
 }
 
 template <int MODEL>

@@ -20,12 +20,18 @@
 // Correctness does not depend on the order being perfectly sorted (a stale order only shortens
 // the runs).
 #pragma once
+#include <cuda.h>
+
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace mpm {
 
 #ifndef MPM_P2G_MINBLK
 #define MPM_P2G_MINBLK 4
+#endif
+#ifndef MPM_P2G_TMA
+#define MPM_P2G_TMA 0  // 1: the 25 particle streams of the block arrive as one 2-D TMA box in shared memory
 #endif
 #ifndef MPM_P2G_CAP
 #define MPM_P2G_CAP 0  // 0 = runs as long as the warp allows
@@ -266,12 +272,31 @@ __device__ __forceinline__ void p2g_list_and_scatter_runs(P2gSmem& sm, uint32_t 
 template <int MODEL, class O, bool EXACT, bool ONE_MAT>
 __global__ void __launch_bounds__(kP2gBlock, MPM_P2G_MINBLK)
 p2g_sched_kernel(Soa p, size_t count, const MpmMaterial* __restrict__ mats, const MpmMaterial mat0, float4* __restrict__ grid,
-                 KParams k) {
+                 KParams k, const __grid_constant__ CUtensorMap tm_streams) {
   __shared__ P2gSmem sm;
   const int tid = threadIdx.x;
   const size_t pi = (size_t)blockIdx.x * kP2gBlock + tid;
+#if MPM_P2G_TMA
+  // The block's 25 x 256 floats as one tiled TMA load: no registers are held while the data
+  // travels, and phase 0 reads its inputs with immediate-offset LDS instead of 25 address
+  // computations + LDG.  Columns beyond the stream length arrive as zeros and are not used.
+  __shared__ __align__(128) float st[NSTREAM * kP2gBlock];
+  __shared__ uint64_t st_bar;
+  if (tid == 0) {
+    mbar_init(&st_bar, 1);
+    mbar_fence_init();
+    mbar_arrive_expect_tx(&st_bar, (uint32_t)sizeof(st));
+    tma_load_2d(st, &tm_streams, (int)(blockIdx.x * kP2gBlock), 0, &st_bar);
+  }
+#endif
   if (tid < 32) sm.hist[tid] = 0;
   __syncthreads();
+#if MPM_P2G_TMA
+  mbar_wait(&st_bar, 0);
+#define MPM_P2G_IN(stream) st[(stream) * kP2gBlock + tid]
+#else
+#define MPM_P2G_IN(stream) p.s(stream)[pi]
+#endif
 
   // ---------------- phase 0: per-particle payload ----------------
   uint32_t key = kInvalidKey;
@@ -279,18 +304,19 @@ p2g_sched_kernel(Soa p, size_t count, const MpmMaterial* __restrict__ mats, cons
     float x[3], v[3];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-      x[a] = p.s(SX + a)[pi];
-      v[a] = p.s(SV + a)[pi];
+      x[a] = MPM_P2G_IN(SX + a);
+      v[a] = MPM_P2G_IN(SV + a);
     }
     Mat3 F, C;
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        F.m[r][c] = p.s(SF + 3 * r + c)[pi];
-        C.m[r][c] = p.s(SC + 3 * r + c)[pi];
+        F.m[r][c] = MPM_P2G_IN(SF + 3 * r + c);
+        C.m[r][c] = MPM_P2G_IN(SC + 3 * r + c);
       }
-    const float Jp = (MODEL == MPM_MODEL_SNOW) ? p.s(SJ)[pi] : 1.0f;  // fixed-corotated never changes Jp
+    const float Jp = (MODEL == MPM_MODEL_SNOW) ? MPM_P2G_IN(SJ) : 1.0f;  // fixed-corotated never changes Jp
+#undef MPM_P2G_IN
     MpmMaterial m;
     if constexpr (ONE_MAT) m = mat0; else m = load_material(mats, p.mat[pi]);  // ONE_MAT: operands straight from the constant bank
     const P2gPayload o = p2g_prepare<MODEL, O, EXACT>(x, v, F, C, Jp, m, k);
@@ -301,7 +327,6 @@ p2g_sched_kernel(Soa p, size_t count, const MpmMaterial* __restrict__ mats, cons
     sm.pay[tid][3] = make_float4(o.cy[2], o.cz[0], o.cz[1], o.cz[2]);
   }
   sm.key[tid] = key;
-
   p2g_list_and_scatter_runs(sm, key, tid, grid, k, BlockBarrier());
 }
 
