@@ -1,4 +1,4 @@
-// Stage (4), production kernel: G2P as a persistent, warp-specialised, TMA-fed pipeline
+// Stage (4), production kernel: G2P as a persistent, TMA-fed pipeline
 // (reference behaviour: src/mpm.cu:109-178, TransferScheme.h:102-142).
 //
 // Why: one thread per particle gathering 27 float4 nodes straight from L2 is latency-bound — 64
@@ -12,15 +12,21 @@
 //     for snow, Jp) are rows 0..12 of the [25][stride] stream tensor: ONE 2-D TMA load.  Nodes
 //     outside the local grid arrive as zeros, which is exactly the reference's stencil clipping
 //     for a gather (src/mpm.cu:137-142), so domain faces and slab edges need no special case.
-//   * CTA = 8 consumer warps + 1 producer warp over a ring of kG2pStages stage buffers with
-//     full/empty mbarriers.  One elected producer lane issues the two TMA loads of tile it+S-1
-//     while the consumers compute tile it; consumers never wait for each other, only for data.
+//   * CTA = 8 warps (one thread per particle of the tile) over a ring of kG2pStages stage buffers
+//     with one "full" mbarrier each.  Thread 0 requests the first kG2pStages tiles; afterwards the
+//     warp that releases a stage LAST (a shared-memory counter per stage tells it so) requests the
+//     tile that goes there next, so the two TMA loads of tile it+S run while tile it is computed and
+//     no warp ever waits for another one, only for data.  (A dedicated producer warp did the same
+//     job at first — MPM_G2P_SELFFEED=0 — but made the CTA 288 threads: 3 CTAs per SM instead of 4.)
 //   * A particle finds its stencil at box[(di+i)*5 + (dj+j)][t+k] where (di, dj, t) is its current
 //     base node relative to the box origin.  The box has one cell of slack on every side, so a
 //     particle that drifted at most one cell in any direction since the re-bin is still inside;
 //     the rest take the generic global-memory gather, which clips like the reference.
-//   * The gather is the separable FFMA2 form (kernels.cuh), reading LDS.128 at compile-time
-//     offsets from one per-particle base address.
+//   * The gather is the separable FFMA2 form (kernels.cuh).
+//   * Node source (MPM_G2P_GATHER): 1 (default) = every thread gathers its 27 nodes from global
+//     memory through L1 — the fastest form measured, because a cell-sorted warp's LDG.128 touches one
+//     or two 128-byte lines (1-2 L1 wavefronts) while an LDS.128 always costs four; 0 = the TMA node
+//     box described above; 2 = a per-warp brick in shared memory (DESIGN.md 3.1 has the numbers).
 #pragma once
 #include <cuda.h>
 
