@@ -126,3 +126,29 @@ def test_cli_rubber_duck_config0(tmp_path):
         tol = 1e-3 if f < 24 else 2e-2   # ~1000 substeps of an elastic body bouncing: stated looser bound
         assert err < tol, (f, err)
     assert "done: 1000 substeps" in r.stdout
+
+
+@pytest.mark.parametrize("scene,N,pc,steps", [("snowman.toml", 64, 500000, 60), ("liquid_bunny.toml", 32, 1000000, 60)])
+def test_readme_scenes_short_horizon(scene, N, pc, steps):
+    """BASELINE.json configs[1] and configs[2] (README.md:15-16 command lines) through the facade:
+    snow plasticity via svd3 on the snowman, high particles-per-cell atomic contention on the bunny.
+    Declared stand-in meshes; per-particle position / velocity error against the oracle."""
+    from mpm_b200 import host
+
+    s = host.Scene("--scene", os.path.join(ROOT, "scenes", scene), "--N", N, "--particle-count", pc)
+    p = s.active_particles()
+    mats = np.array(s.materials.tolist(), np.float32)
+    assert len(p) > 5000
+    ppc = len(p) / max(1, len(np.unique(ol.cell_keys(p, float(DT), N))))
+    s.init_cuda()
+    s.advance(steps)
+    s.sync_device()
+    got = s.active_particles()
+    ref, _ = ol.advance(p.copy(), mats, float(DT), N, ol.SNOW, steps)
+    assert len(got) == len(ref)
+    pos = np.abs(got["x"].astype(np.float64) - ref["x"]).max() * N
+    vel = np.linalg.norm(got["v"].astype(np.float64) - ref["v"], axis=1) / np.maximum(np.linalg.norm(ref["v"], axis=1), 1e-1)
+    assert pos < 1e-3, pos
+    assert np.quantile(vel, 0.999) < 1e-2, np.quantile(vel, 0.999)
+    assert np.abs(got["Jp"].astype(np.float64) - ref["Jp"]).max() < 1e-3
+    print(f"{scene}: {len(p)} particles, {ppc:.1f} per occupied cell, max |dx|/dx = {pos:.2e}")
