@@ -189,6 +189,8 @@ def main():
     ap.add_argument("--g2p", default="tile", choices=["tile", "direct"], help="G2P kernel (MpmParams.g2p_mode)")
     ap.add_argument("--p2g", default="runs", choices=["runs", "direct"], help="P2G kernel (MpmParams.p2g_mode)")
     ap.add_argument("--fuse", default="off", choices=["g2p2g", "off"], help="substep pipeline (MpmParams.fuse_mode)")
+    ap.add_argument("--rebin-permille", type=int, default=0,
+                    help="MpmParams.rebin_permille: also re-bin on measured disorder (0 = fixed cadence only, the default)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N > 1: weak = 2^26 particles per GPU (default), strong = 2^26 particles in total at N = 256")
     ap.add_argument("--model", default="fixed_corotated", choices=["fixed_corotated", "snow"],
@@ -238,7 +240,8 @@ def main():
                        x_begin=xb, x_end=xe, device=local_rank, capacity=cap,
                        p2g_mode=mpm_b200.P2G_RUNS if args.p2g == "runs" else mpm_b200.P2G_DIRECT,
                        g2p_mode=mpm_b200.G2P_TILE if args.g2p == "tile" else mpm_b200.G2P_DIRECT,
-                       fuse_mode=mpm_b200.FUSE_G2P2G if args.fuse == "g2p2g" else mpm_b200.FUSE_OFF)
+                       fuse_mode=mpm_b200.FUSE_G2P2G if args.fuse == "g2p2g" else mpm_b200.FUSE_OFF,
+                       rebin_permille=args.rebin_permille)
     if world > 1:
         from mpm_b200 import slabs as _slabs
 
@@ -343,7 +346,7 @@ def main():
                                    + (")" if world == 1 else (f" scaled weakly to {world} GPUs: 2^26 particles and ~2^24 nodes per GPU)" if args.scaling == "weak"
                                                               else f" strong scaling: the same block cut into {world} slabs)")),
                        "N": N, "particles": int(P_all), "grid_nodes": int(G_all), "dt": dt, "model": args.model,
-                       "svd_mode": args.svd, "sort_every": args.sort_every, "p2g": args.p2g, "g2p": args.g2p, "fuse": args.fuse, "slabs": slabs if world > 1 else None,
+                       "svd_mode": args.svd, "sort_every": args.sort_every, "rebin_permille": args.rebin_permille, "p2g": args.p2g, "g2p": args.g2p, "fuse": args.fuse, "slabs": slabs if world > 1 else None,
                        "l2": "inputs (6.7 GB particles + 268 MB grid per GPU) are far larger than the 126 MB L2; no flush"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "substep_roofline": substep_roofline, "stage_ms": stage_ms,

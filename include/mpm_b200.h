@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define MPM_B200_ABI_VERSION 3
+#define MPM_B200_ABI_VERSION 4
 
 /* which MaterialModel alias the kernels are instantiated for (reference include/mpm.cuh:25) */
 enum { MPM_MODEL_SNOW = 0, MPM_MODEL_FIXED_COROTATED = 1 };
@@ -86,6 +86,10 @@ typedef struct MpmParams {
                            may drift out of its slab between re-bins (0 = default: 1 for slabs) */
   uint32_t g2p_mode;    /* MPM_G2P_* */
   uint32_t fuse_mode;   /* MPM_FUSE_* */
+  uint32_t rebin_permille; /* 0 = fixed cadence only.  > 0: also re-bin as soon as the cell crossings counted by G2P
+                           since the last re-bin exceed this many per mille of the particle count (needs
+                           G2P_TILE, separate kernels); sort_every = 0 then means "only on demand" */
+  uint32_t reserved_;   /* must be 0 */
 } MpmParams;
 
 typedef struct MpmSim MpmSim;
@@ -134,6 +138,7 @@ int mpm_sync(MpmSim* sim);
 double mpm_time(const MpmSim* sim);           /* Simulation::t */
 uint64_t mpm_substeps_done(const MpmSim* sim);
 uint64_t mpm_kernel_launches(const MpmSim* sim); /* kernels this handle has launched so far */
+uint64_t mpm_rebins_done(const MpmSim* sim);     /* re-bins (sort + permute) so far, the one at upload included */
 
 /* single stages, for parity tests and profiling (same kernels mpm_advance runs) */
 int mpm_stage_sort(MpmSim* sim);        /* north-star stage (1): cell keys, radix sort, SoA permute */

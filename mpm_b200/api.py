@@ -27,7 +27,8 @@ class MpmParams(ctypes.Structure):
                 ("svd_mode", ctypes.c_uint32), ("sort_every", ctypes.c_uint32), ("x_begin", ctypes.c_uint32),
                 ("x_end", ctypes.c_uint32), ("device", ctypes.c_int32), ("capacity", ctypes.c_uint64),
                 ("p2g_mode", ctypes.c_uint32), ("ghost", ctypes.c_uint32), ("g2p_mode", ctypes.c_uint32),
-                ("fuse_mode", ctypes.c_uint32)]
+                ("fuse_mode", ctypes.c_uint32), ("rebin_permille", ctypes.c_uint32),
+                ("reserved_", ctypes.c_uint32)]
 
 
 class MpmError(RuntimeError):
@@ -57,6 +58,8 @@ def lib():
         L.mpm_substeps_done.argtypes = [_vp]
         L.mpm_kernel_launches.restype = ctypes.c_uint64
         L.mpm_kernel_launches.argtypes = [_vp]
+        L.mpm_rebins_done.restype = ctypes.c_uint64
+        L.mpm_rebins_done.argtypes = [_vp]
         L.mpm_stream.restype = _vp
         L.mpm_stream.argtypes = [_vp]
         L.mpm_destroy.restype = None
@@ -106,10 +109,10 @@ class Sim:
     """One handle = one device.  Mirrors the device half of the reference's Simulation class."""
 
     def __init__(self, N, dt, materials, model=SNOW, svd_mode=SVD_EXACT, sort_every=0, x_begin=0, x_end=0,
-                 device=-1, capacity=0, p2g_mode=P2G_RUNS, ghost=0, g2p_mode=G2P_TILE, fuse_mode=FUSE_OFF):
+                 device=-1, capacity=0, p2g_mode=P2G_RUNS, ghost=0, g2p_mode=G2P_TILE, fuse_mode=FUSE_OFF, rebin_permille=0):
         self._h = _vp()
         mats = np.ascontiguousarray(materials, np.float32).reshape(-1, 7)
-        self.params = MpmParams(dt, N, model, svd_mode, sort_every, x_begin, x_end, device, capacity, p2g_mode, ghost, g2p_mode, fuse_mode)
+        self.params = MpmParams(dt, N, model, svd_mode, sort_every, x_begin, x_end, device, capacity, p2g_mode, ghost, g2p_mode, fuse_mode, rebin_permille, 0)
         rc = lib().mpm_create(ctypes.byref(self.params), _ptr(mats), mats.shape[0], ctypes.byref(self._h))
         if rc:
             raise MpmError(lib().mpm_last_error(None).decode())
@@ -197,6 +200,10 @@ class Sim:
     @property
     def launches(self):
         return lib().mpm_kernel_launches(self._h)
+
+    @property
+    def rebins(self):
+        return lib().mpm_rebins_done(self._h)
 
     @property
     def stream(self):

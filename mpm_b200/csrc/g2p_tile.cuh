@@ -142,10 +142,10 @@ __device__ __forceinline__ void g2p_gather27(const float4* __restrict__ tp, long
   o.B.m[0][2] = lo2(B2xy); o.B.m[1][2] = hi2(B2xy); o.B.m[2][2] = B2z;
 }
 
-template <int MODEL, class O, int LT>
+template <int MODEL, class O, int LT, bool COUNT_MOVED>
 __device__ __forceinline__ void g2p_tile_compute(const Soa& p, const MpmMaterial* __restrict__ mats, const float4* __restrict__ grid,
                                                  const KParams& k, const TileHeader& h, const float4* __restrict__ box,
-                                                 float4* __restrict__ wtile, const float* __restrict__ ps, int tid) {
+                                                 float4* __restrict__ wtile, const float* __restrict__ ps, int tid, unsigned& moved) {
   const bool live = tid < h.n;
   const size_t pi = (size_t)h.start + tid;
   uint8_t mat_id = 0;
@@ -263,11 +263,15 @@ __device__ __forceinline__ void g2p_tile_compute(const Soa& p, const MpmMaterial
     snow_plasticity<O>(F, Jp, m);
     MPM_STP(p.s(SJ) + pi, Jp);
   }
+  bool crossed = false;  // did the advection take the particle into another cell (rebin_permille, mpm_b200.h)
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
-    MPM_STP(p.s(SX + a) + pi, x[a] + k.dt * v[a]);
+    const float xn = x[a] + k.dt * v[a];
+    if (COUNT_MOVED) crossed = crossed || ((int)(xn * k.dx_inv - 0.5f) != base[a]);
+    MPM_STP(p.s(SX + a) + pi, xn);
     MPM_STP(p.s(SV + a) + pi, v[a]);
   }
+  if (COUNT_MOVED) moved += crossed ? 1u : 0u;
 #if defined(MPM_G2P_EXP) && (MPM_G2P_EXP & 2)  // experiment: 6 of the 24 output streams only
   if (F.m[0][0] + C.m[1][1] + F.m[2][2] + C.m[0][2] == 12345.f) MPM_STP(p.s(SF) + pi, 0.f);
 #else
@@ -282,11 +286,12 @@ __device__ __forceinline__ void g2p_tile_compute(const Soa& p, const MpmMaterial
 }
 
 // Persistent CTAs: tile `it` of this CTA = blockIdx.x + it * gridDim.x.
-template <int MODEL, class O, int LT>
+template <int MODEL, class O, int LT, bool COUNT_MOVED>
 __global__ void __launch_bounds__(kG2pThreads, MPM_G2P_SELFFEED ? 4 : MPM_G2P_TILE_MINBLK)
 g2p_tile_kernel(Soa p, const MpmMaterial* __restrict__ mats, const float4* __restrict__ grid, KParams k,
                 const TileDesc* __restrict__ tiles, const uint32_t* __restrict__ n_tiles_ptr,
-                const __grid_constant__ CUtensorMap tm_grid, const __grid_constant__ CUtensorMap tm_streams) {
+                const __grid_constant__ CUtensorMap tm_grid, const __grid_constant__ CUtensorMap tm_streams,
+                unsigned long long* __restrict__ moved_total) {
   using L = G2pTileLayout<MODEL>;
   static_assert(SX == 0 && SF == 3 && SJ == 12, "G2P reads stream rows 0..12 as one TMA box");
   extern __shared__ unsigned char smem_dyn[];
@@ -355,13 +360,14 @@ g2p_tile_kernel(Soa p, const MpmMaterial* __restrict__ mats, const float4* __res
 #endif
   // ---- consumer warps ----
   int it = 0;
+  unsigned moved = 0;  // particles of this thread that changed cell in this substep
   for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
     const int s = it % kG2pStages;
     mbar_wait(full + s, (uint32_t)((it / kG2pStages) & 1));
     const unsigned char* st = smem + s * kStage;
-    g2p_tile_compute<MODEL, O, LT>(p, mats, grid, k, hdr[s], reinterpret_cast<const float4*>(st),
+    g2p_tile_compute<MODEL, O, LT, COUNT_MOVED>(p, mats, grid, k, hdr[s], reinterpret_cast<const float4*>(st),
                                    bricks + (tid >> 5) * (kWarpBrickX * kWarpBrickY * kWarpBrickZ),
-                                   reinterpret_cast<const float*>(st + L::box_bytes(LT)), tid);
+                                   reinterpret_cast<const float*>(st + L::box_bytes(LT)), tid, moved);
     __syncwarp();  // stage s and the warp's brick are free again
 #if MPM_G2P_SELFFEED
     if ((tid & 31) == 0) {
@@ -379,6 +385,10 @@ g2p_tile_kernel(Soa p, const MpmMaterial* __restrict__ mats, const float4* __res
 #else
     if ((tid & 31) == 0) mbar_arrive(empty + s);
 #endif
+  }
+  if (COUNT_MOVED) {
+    moved = __reduce_add_sync(0xffffffffu, moved);
+    if ((tid & 31) == 0 && moved) atomicAdd(moved_total, (unsigned long long)moved);
   }
 }
 

@@ -89,6 +89,15 @@ struct MpmSim {
   size_t aos_stage_cap = 0;
   unsigned long long* d_counter = nullptr;
 
+  // adaptive re-bin (MpmParams.rebin_permille): cell crossings counted by the G2P tile kernel since the
+  // last re-bin, read back asynchronously (never waited for)
+  unsigned long long* d_moved = nullptr;
+  unsigned long long* h_moved = nullptr;  // pinned
+  cudaEvent_t moved_ev = nullptr;
+  bool moved_pending = false;
+  unsigned long long moved_seen = 0;
+  uint64_t rebins = 0;
+
   uint64_t substeps = 0;
   uint64_t steps_since_sort = 0;
   uint64_t launches = 0;
@@ -264,6 +273,10 @@ int build_tiles(MpmSim* sim) {
 int do_sort(MpmSim* sim, bool partial = false) {
   StageTimer tm(sim, MPM_STAGE_SORT);
   sim->steps_since_sort = 0;
+  sim->rebins++;
+  sim->moved_seen = 0;
+  sim->moved_pending = false;
+  if (sim->d_moved) CK(cudaMemsetAsync(sim->d_moved, 0, sizeof(unsigned long long), sim->stream));
   size_t n_dead = 0;
   if (sim->comm.active()) {  // leavers out (tombstoned), arrivals appended, before the re-bin
     if (sim->comm.migrate(sim->soa[sim->cur], &sim->count, sim->capacity, sim->k, sim->stream, &sim->launches, &n_dead))
@@ -356,20 +369,24 @@ int do_grid(MpmSim* sim) {
   return 0;
 }
 
-template <int MODEL, class O, int LT>
-void launch_g2p_tile(MpmSim* sim) {
+template <int MODEL, class O, int LT, bool COUNT_MOVED>
+void launch_g2p_tile_impl(MpmSim* sim) {
   const size_t smem = G2pTileLayout<MODEL>::bytes(LT);
   static int per_sm = 0;  // per instantiation
   if (!per_sm) {
-    cudaFuncSetAttribute(g2p_tile_kernel<MODEL, O, LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, g2p_tile_kernel<MODEL, O, LT>, kG2pThreads, smem);
+    cudaFuncSetAttribute(g2p_tile_kernel<MODEL, O, LT, COUNT_MOVED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, g2p_tile_kernel<MODEL, O, LT, COUNT_MOVED>, kG2pThreads, smem);
     per_sm = std::max(per_sm, 1);
   }
   const size_t max_tiles = sim->count / kTileMax + sim->n_rows + 1;
   const unsigned ctas = (unsigned)std::min<size_t>(max_tiles, (size_t)sim->n_sms * per_sm);
-  g2p_tile_kernel<MODEL, O, LT><<<ctas, kG2pThreads, smem, sim->stream>>>(
+  g2p_tile_kernel<MODEL, O, LT, COUNT_MOVED><<<ctas, kG2pThreads, smem, sim->stream>>>(
       sim->soa[sim->cur], sim->mats, sim->grid, sim->k, sim->tiles, sim->d_n_tiles, sim->tm_grid[LT == kLtSmall ? 0 : 1],
-      sim->tm_streams[sim->cur][MODEL == MPM_MODEL_SNOW ? 1 : 0]);
+      sim->tm_streams[sim->cur][MODEL == MPM_MODEL_SNOW ? 1 : 0], sim->d_moved);
+}
+template <int MODEL, class O, int LT>
+void launch_g2p_tile(MpmSim* sim) {  // the cell-crossing count costs a register the default path cannot spare
+  if (sim->par.rebin_permille) launch_g2p_tile_impl<MODEL, O, LT, true>(sim); else launch_g2p_tile_impl<MODEL, O, LT, false>(sim);
 }
 
 template <int MODEL>
@@ -479,7 +496,7 @@ int mpm_create(const MpmParams* params, const MpmMaterial* materials, int n_mate
   if (params->N < 4) return fail(nullptr, "mpm_create: N must be >= 4");
   if (n_materials < 1 || n_materials > 256 || !materials) return fail(nullptr, "mpm_create: need 1..256 materials");
   if (params->model > MPM_MODEL_FIXED_COROTATED || params->svd_mode > MPM_SVD_FAST || params->p2g_mode > MPM_P2G_DIRECT ||
-      params->g2p_mode > MPM_G2P_DIRECT || params->fuse_mode > MPM_FUSE_G2P2G)
+      params->g2p_mode > MPM_G2P_DIRECT || params->fuse_mode > MPM_FUSE_G2P2G || params->rebin_permille > 1000 || params->reserved_ != 0)
     return fail(nullptr, "mpm_create: bad model / svd_mode / p2g_mode / g2p_mode / fuse_mode");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -560,6 +577,10 @@ int mpm_create(const MpmParams* params, const MpmMaterial* materials, int n_mate
   CKC(cudaMalloc(&sim->d_span, 2 * sizeof(unsigned int)));
   CKC(cudaMallocHost(&sim->h_span, 2 * sizeof(unsigned int)));
   CKC(cudaEventCreateWithFlags(&sim->span_ev, cudaEventDisableTiming));
+  CKC(cudaMalloc(&sim->d_moved, sizeof(unsigned long long)));
+  CKC(cudaMemsetAsync(sim->d_moved, 0, sizeof(unsigned long long), sim->stream));
+  CKC(cudaMallocHost(&sim->h_moved, sizeof(unsigned long long)));
+  CKC(cudaEventCreateWithFlags(&sim->moved_ev, cudaEventDisableTiming));
   if (params->capacity) {
     if (int rc = ensure_capacity(sim, (size_t)params->capacity)) {
       g_create_error = sim->err;
@@ -594,6 +615,9 @@ void mpm_destroy(MpmSim* sim) {
   cudaFree(sim->row_first);
   cudaFree(sim->tile_base);
   cudaFree(sim->d_n_tiles);
+  cudaFree(sim->d_moved);
+  if (sim->h_moved) cudaFreeHost(sim->h_moved);
+  if (sim->moved_ev) cudaEventDestroy(sim->moved_ev);
   if (sim->h_span) cudaFreeHost(sim->h_span);
   if (sim->span_ev) cudaEventDestroy(sim->span_ev);
   if (sim->ev[0]) cudaEventDestroy(sim->ev[0]);
@@ -722,6 +746,7 @@ size_t mpm_grid_nodes(const MpmSim* sim) { return sim ? sim->grid_nodes : 0; }
 double mpm_time(const MpmSim* sim) { return sim ? sim->t : 0.0; }
 uint64_t mpm_substeps_done(const MpmSim* sim) { return sim ? sim->substeps : 0; }
 uint64_t mpm_kernel_launches(const MpmSim* sim) { return sim ? sim->launches : 0; }
+uint64_t mpm_rebins_done(const MpmSim* sim) { return sim ? sim->rebins : 0; }
 void* mpm_stream(MpmSim* sim) { return sim ? (void*)sim->stream : nullptr; }
 
 int mpm_stage_sort(MpmSim* sim) { if (!sim) return 1; CK(cudaSetDevice(sim->device)); return do_sort(sim); }
@@ -737,7 +762,18 @@ int mpm_advance(MpmSim* sim, int n_substeps) {
   CK(cudaSetDevice(sim->device));
   for (int s = 0; s < n_substeps; ++s) {
     bool rebin_late = false;
-    if (sim->par.sort_every && sim->steps_since_sort >= sim->par.sort_every) {
+    bool due = sim->par.sort_every && sim->steps_since_sort >= sim->par.sort_every;
+    const bool adaptive = sim->par.rebin_permille && !sim->fused && sim->par.g2p_mode == MPM_G2P_TILE;
+    if (adaptive) {
+      // re-bin on measured disorder: the count of cell crossings since the last re-bin arrives a
+      // substep or two late (asynchronous read-back), which is early enough for a locality heuristic
+      if (sim->moved_pending && cudaEventQuery(sim->moved_ev) == cudaSuccess) {
+        sim->moved_pending = false;
+        sim->moved_seen = *sim->h_moved;
+      }
+      due = due || (sim->steps_since_sort > 0 && sim->moved_seen * 1000ull >= (unsigned long long)sim->par.rebin_permille * sim->count && sim->count > 0);
+    }
+    if (due) {
       // (slab handles migrate whole particle records at the re-bin: v and C are still the previous
       // substep's there, so leavers carry a complete state; the fused pipeline has no such gap)
       rebin_late = !sim->fused;
@@ -773,6 +809,11 @@ int mpm_advance(MpmSim* sim, int n_substeps) {
         if (int rc = do_sort(sim, true)) return rc;
       }
       if (int rc = do_g2p(sim)) return rc;
+      if (adaptive && !sim->moved_pending) {
+        CK(cudaMemcpyAsync(sim->h_moved, sim->d_moved, sizeof(unsigned long long), cudaMemcpyDeviceToHost, sim->stream));
+        CK(cudaEventRecord(sim->moved_ev, sim->stream));
+        sim->moved_pending = true;
+      }
     }
     sim->t += (double)sim->par.dt;
     sim->substeps++;

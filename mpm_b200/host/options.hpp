@@ -3,7 +3,7 @@
 // Accepted forms: --name value, --name=value.  A parse error prints a message and exits with
 // status 1, like the reference (options.h:48-51).  Extensions (not in the reference, all optional):
 // --steps (stop after this many substeps; the reference loops until killed), --svd exact|fast,
-// --sort-every, --sync-every, --frame-rate.
+// --sort-every, --rebin-permille, --sync-every, --frame-rate.
 #pragma once
 #include <cstdint>
 #include <cstdlib>
@@ -36,6 +36,7 @@ struct CLIOptions {
   long long steps = -1;
   std::string svd = "exact";
   u32 sort_every = 8;
+  u32 rebin_permille = 0;  // MpmParams.rebin_permille
   u32 sync_every = 20;  // src/main.cu:99
   u32 frame_rate = 240; // src/main.cu:8
   std::string particle_format = "pda";
@@ -91,6 +92,7 @@ struct CLIOptions {
         else if (k == "steps") steps = std::stoll(v);
         else if (k == "svd") svd = v;
         else if (k == "sort-every") sort_every = to_u32(v);
+        else if (k == "rebin-permille") rebin_permille = to_u32(v);
         else if (k == "sync-every") sync_every = to_u32(v);
         else if (k == "frame-rate") frame_rate = to_u32(v);
         else if (k == "particle-format") particle_format = v;

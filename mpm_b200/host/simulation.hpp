@@ -129,6 +129,7 @@ class Simulation {
     p.model = MPM_MODEL_SNOW;  // mpm.cuh:25: MaterialModel = MMSnow
     p.svd_mode = opts_.svd == "fast" ? MPM_SVD_FAST : MPM_SVD_EXACT;
     p.sort_every = opts_.sort_every;
+    p.rebin_permille = opts_.rebin_permille;
     p.device = -1;
     p.capacity = std::max<size_t>(getFullParticleCount(), 1);  // every object fits: activation never reallocates
     if (material_models.empty()) throw std::runtime_error("no materials");
@@ -155,7 +156,7 @@ class Simulation {
       for (Particle& q : objects[o].particles) q = host_[i++];
   }
 
-  // positions only (12 B/particle) in getActiveParticleList order: what a viewer needs
+  // positions only (12 B/particle) in upload order (= getActiveParticleList order until an object is appended): what a viewer needs
   void syncPositions(std::vector<float>& xyz) {
     xyz.resize(3 * uploaded_count());
     size_t n = 0;

@@ -231,6 +231,30 @@ def test_fused_pipeline_matches_separate_kernels(kind, sort_every):
     assert np.abs(a["v"].astype(np.float64) - ref["v"]).max() <= 1e-3 * np.abs(ref["v"]).max()
 
 
+def test_adaptive_rebin_on_measured_disorder():
+    """MpmParams.rebin_permille: re-bin when the cell crossings counted by G2P exceed a share of the
+    particles.  A thrown ball triggers re-bins without any fixed cadence and the result still matches
+    the oracle; a ball at rest in free fall for a few substeps never re-bins after the upload."""
+    N, steps = 32, 100
+    p, mats = scenes.two_spheres(N, kind=ol.SNOW, perturb=False)
+    sim = _sim(N, mats, ol.SNOW, 0, sort_every=0, rebin_permille=20)
+    sim.upload(p)
+    assert sim.rebins == 1
+    sim.advance(steps)
+    got = sim.download()
+    n_rebins = sim.rebins
+    assert 2 <= n_rebins < steps // 2, n_rebins
+    ref, _ = ol.advance(p.copy(), mats, DT, N, ol.SNOW, steps)
+    assert np.abs(got["x"].astype(np.float64) - ref["x"]).max() * N < 1e-3
+    rest = p[p["v"][:, 1] == 0].copy()
+    sim2 = _sim(N, mats, ol.SNOW, 0, sort_every=0, rebin_permille=20)
+    sim2.upload(rest)
+    sim2.advance(10)
+    sim2.sync()
+    assert sim2.rebins == 1
+    print(f"adaptive re-bin: {n_rebins - 1} re-bins in {steps} substeps of the two-ball impact")
+
+
 def test_positions_readback_blocking_and_async():
     """positions-only read-back (12 B/particle) in upload order, blocking and queued."""
     N = 32
