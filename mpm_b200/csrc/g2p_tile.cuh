@@ -52,6 +52,12 @@ constexpr int kBoxRows = kBoxW * kBoxW;
 #define MPM_G2P_GATHER 1  // node source: 0 = 5x5xLT TMA box per tile, 1 = global memory per thread, 2 = per-warp brick
 #endif
 #define MPM_G2P_BOX (MPM_G2P_GATHER == 0)
+// With the per-thread global gather nothing ties a tile to one grid row, so tiles are simply the
+// 256-particle blocks of the sorted order: full lanes (row tiles average 228 of 256 particles on the
+// benchmark block) and no tile descriptors.  The shared-memory node sources need row tiles.
+#ifndef MPM_G2P_FLAT_TILES
+#define MPM_G2P_FLAT_TILES (MPM_G2P_GATHER == 1)
+#endif
 constexpr int kWarpBrickX = 4, kWarpBrickY = 4, kWarpBrickZ = 16;  // nodes; 4 KB of shared memory per warp
 constexpr int kG2pStages = MPM_G2P_STAGES;
 #ifndef MPM_G2P_SELFFEED
@@ -291,7 +297,7 @@ __global__ void __launch_bounds__(kG2pThreads, MPM_G2P_SELFFEED ? 4 : MPM_G2P_TI
 g2p_tile_kernel(Soa p, const MpmMaterial* __restrict__ mats, const float4* __restrict__ grid, KParams k,
                 const TileDesc* __restrict__ tiles, const uint32_t* __restrict__ n_tiles_ptr,
                 const __grid_constant__ CUtensorMap tm_grid, const __grid_constant__ CUtensorMap tm_streams,
-                unsigned long long* __restrict__ moved_total) {
+                unsigned long long* __restrict__ moved_total, size_t count) {
   using L = G2pTileLayout<MODEL>;
   static_assert(SX == 0 && SF == 3 && SJ == 12, "G2P reads stream rows 0..12 as one TMA box");
   extern __shared__ unsigned char smem_dyn[];
@@ -302,7 +308,7 @@ g2p_tile_kernel(Soa p, const MpmMaterial* __restrict__ mats, const float4* __res
   uint64_t* full = reinterpret_cast<uint64_t*>(hdr + kG2pStages);
   uint64_t* empty = full + kG2pStages;
   const int tid = threadIdx.x;
-  const uint32_t n_tiles = *n_tiles_ptr;
+  const uint32_t n_tiles = MPM_G2P_FLAT_TILES ? (uint32_t)((count + kTile - 1) / kTile) : *n_tiles_ptr;
   if (tid == 0) {
     for (int s = 0; s < kG2pStages; ++s) {
       mbar_init(full + s, 1);
@@ -314,7 +320,14 @@ g2p_tile_kernel(Soa p, const MpmMaterial* __restrict__ mats, const float4* __res
 
   // one TMA request: header + stream rows (+ node box) of tile t into stage s
   auto issue = [&](uint32_t t, int s) {
-    const TileDesc d = tiles[t];
+    TileDesc d;
+    if (MPM_G2P_FLAT_TILES) {
+      d.start = t * (uint32_t)kTile;
+      d.n = (uint32_t)min((size_t)kTile, count - (size_t)d.start);
+      d.kfirst = d.klast = 0;
+    } else {
+      d = tiles[t];
+    }
     const uint32_t row = d.kfirst / (uint32_t)k.N;
     TileHeader h;
     h.z0b = (int)(d.kfirst - row * (uint32_t)k.N) - 1;

@@ -313,7 +313,10 @@ int do_sort(MpmSim* sim, bool partial = false) {
   sim->launches++;
   sim->cur ^= 1;
   sim->count = n - n_dead;  // tombstones were sorted behind the live particles
-  if (int rc = build_tiles(sim)) return rc;
+  // row tiles are needed by the fused kernel and by the shared-memory node sources of G2P only
+  if (sim->fused || !MPM_G2P_FLAT_TILES) {
+    if (int rc = build_tiles(sim)) return rc;
+  }
   CK(cudaGetLastError());
   return 0;
 }
@@ -378,11 +381,11 @@ void launch_g2p_tile_impl(MpmSim* sim) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, g2p_tile_kernel<MODEL, O, LT, COUNT_MOVED>, kG2pThreads, smem);
     per_sm = std::max(per_sm, 1);
   }
-  const size_t max_tiles = sim->count / kTileMax + sim->n_rows + 1;
+  const size_t max_tiles = MPM_G2P_FLAT_TILES ? (sim->count + kTile - 1) / kTile : sim->count / kTileMax + sim->n_rows + 1;
   const unsigned ctas = (unsigned)std::min<size_t>(max_tiles, (size_t)sim->n_sms * per_sm);
   g2p_tile_kernel<MODEL, O, LT, COUNT_MOVED><<<ctas, kG2pThreads, smem, sim->stream>>>(
       sim->soa[sim->cur], sim->mats, sim->grid, sim->k, sim->tiles, sim->d_n_tiles, sim->tm_grid[LT == kLtSmall ? 0 : 1],
-      sim->tm_streams[sim->cur][MODEL == MPM_MODEL_SNOW ? 1 : 0], sim->d_moved);
+      sim->tm_streams[sim->cur][MODEL == MPM_MODEL_SNOW ? 1 : 0], sim->d_moved, sim->count);
 }
 template <int MODEL, class O, int LT>
 void launch_g2p_tile(MpmSim* sim) {  // the cell-crossing count costs a register the default path cannot spare
