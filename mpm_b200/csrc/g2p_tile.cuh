@@ -55,6 +55,9 @@ constexpr int kBoxRows = kBoxW * kBoxW;
 // With the per-thread global gather nothing ties a tile to one grid row, so tiles are simply the
 // 256-particle blocks of the sorted order: full lanes (row tiles average 228 of 256 particles on the
 // benchmark block) and no tile descriptors.  The shared-memory node sources need row tiles.
+#ifndef MPM_G2P_DYNAMIC
+#define MPM_G2P_DYNAMIC 1  // 1: after the first ring fill, tiles are handed out by a global counter (needs SELFFEED)
+#endif
 #ifndef MPM_G2P_FLAT_TILES
 #define MPM_G2P_FLAT_TILES (MPM_G2P_GATHER == 1)
 #endif
@@ -297,7 +300,7 @@ __global__ void __launch_bounds__(kG2pThreads, MPM_G2P_SELFFEED ? 4 : MPM_G2P_TI
 g2p_tile_kernel(Soa p, const MpmMaterial* __restrict__ mats, const float4* __restrict__ grid, KParams k,
                 const TileDesc* __restrict__ tiles, const uint32_t* __restrict__ n_tiles_ptr,
                 const __grid_constant__ CUtensorMap tm_grid, const __grid_constant__ CUtensorMap tm_streams,
-                unsigned long long* __restrict__ moved_total, size_t count) {
+                unsigned long long* __restrict__ moved_total, size_t count, unsigned int* __restrict__ tile_counters, int parity) {
   using L = G2pTileLayout<MODEL>;
   static_assert(SX == 0 && SF == 3 && SJ == 12, "G2P reads stream rows 0..12 as one TMA box");
   extern __shared__ unsigned char smem_dyn[];
@@ -352,8 +355,14 @@ g2p_tile_kernel(Soa p, const MpmMaterial* __restrict__ mats, const float4* __res
     for (int s = 0; s < kG2pStages; ++s) {
       rel[2 * s] = 0;
       const uint32_t t = blockIdx.x + (uint32_t)s * gridDim.x;
-      if (t < n_tiles) issue(t, s);
+      if (t < n_tiles) {
+        issue(t, s);
+      } else if (MPM_G2P_DYNAMIC) {  // end marker
+        hdr[s].n = -1;
+        mbar_arrive(full + s);
+      }
     }
+    if (MPM_G2P_DYNAMIC && blockIdx.x == 0) tile_counters[parity ^ 1] = 0;  // the next launch's counter
   }
   __syncthreads();
 #else
@@ -374,9 +383,10 @@ g2p_tile_kernel(Soa p, const MpmMaterial* __restrict__ mats, const float4* __res
   // ---- consumer warps ----
   int it = 0;
   unsigned moved = 0;  // particles of this thread that changed cell in this substep
-  for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+  for (uint32_t t = blockIdx.x; MPM_G2P_DYNAMIC || t < n_tiles; t += gridDim.x, ++it) {
     const int s = it % kG2pStages;
     mbar_wait(full + s, (uint32_t)((it / kG2pStages) & 1));
+    if (MPM_G2P_DYNAMIC && hdr[s].n < 0) break;  // no more tiles for this CTA
     const unsigned char* st = smem + s * kStage;
     g2p_tile_compute<MODEL, O, LT, COUNT_MOVED>(p, mats, grid, k, hdr[s], reinterpret_cast<const float4*>(st),
                                    bricks + (tid >> 5) * (kWarpBrickX * kWarpBrickY * kWarpBrickZ),
@@ -388,10 +398,15 @@ g2p_tile_kernel(Soa p, const MpmMaterial* __restrict__ mats, const float4* __res
       if (atomicAdd(&rel[2 * s], 1u) == kTile / 32 - 1) {
         rel[2 * s] = 0;
         __threadfence_block();
-        const uint32_t tn = t + (uint32_t)kG2pStages * gridDim.x;
+        // static: the tile kG2pStages rounds ahead; dynamic: the next tile nobody has taken yet
+        const uint32_t tn = MPM_G2P_DYNAMIC ? (uint32_t)kG2pStages * gridDim.x + atomicAdd(&tile_counters[parity], 1u)
+                                            : t + (uint32_t)kG2pStages * gridDim.x;
         if (tn < n_tiles) {
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the warps' reads of the stage before the copy engine's writes
           issue(tn, s);
+        } else if (MPM_G2P_DYNAMIC) {
+          hdr[s].n = -1;
+          mbar_arrive(full + s);
         }
       }
     }

@@ -91,6 +91,8 @@ struct MpmSim {
 
   // adaptive re-bin (MpmParams.rebin_permille): cell crossings counted by the G2P tile kernel since the
   // last re-bin, read back asynchronously (never waited for)
+  unsigned int* d_tile_counters = nullptr;  // [2], used alternately by the dynamic tile scheduler of G2P
+  int tile_parity = 0;
   unsigned long long* d_moved = nullptr;
   unsigned long long* h_moved = nullptr;  // pinned
   cudaEvent_t moved_ev = nullptr;
@@ -270,7 +272,7 @@ int build_tiles(MpmSim* sim) {
 }
 
 // partial: called between the grid update and G2P, permutes only what G2P reads (sort.cuh)
-int do_sort(MpmSim* sim, bool partial = false) {
+int do_sort(MpmSim* sim, bool partial = false, bool keys_ready = false) {
   StageTimer tm(sim, MPM_STAGE_SORT);
   sim->steps_since_sort = 0;
   sim->rebins++;
@@ -290,8 +292,10 @@ int do_sort(MpmSim* sim, bool partial = false) {
   Soa& src = sim->soa[sim->cur];
   const uint32_t dead_key = 1u << sim->key_bits;
   const int sort_bits = sim->key_bits + (sim->comm.active() ? 1 : 0);
-  cell_key_kernel<<<blocks_for(n, 256), 256, 0, sim->stream>>>(src, n, sim->k, sim->keys[0], sim->vals[0], dead_key);
-  sim->launches++;
+  if (!keys_ready) {  // else the P2G of this substep wrote them (p2g_sched.cuh, KEYS)
+    cell_key_kernel<<<blocks_for(n, 256), 256, 0, sim->stream>>>(src, n, sim->k, sim->keys[0], sim->vals[0], dead_key);
+    sim->launches++;
+  }
   const int n_tiles = (int)((n + kSortTile - 1) / kSortTile);
   const size_t table_len = (size_t)n_tiles * kRadix;
   const unsigned scan_blocks = blocks_for(table_len, kScanTile);
@@ -327,24 +331,31 @@ int do_reset(MpmSim* sim, float4* grid = nullptr) {
   return 0;
 }
 
-template <int MODEL, class O, bool EXACT>
-void launch_p2g_sched(MpmSim* sim) {
+template <int MODEL, class O, bool EXACT, bool KEYS>
+void launch_p2g_sched_k(MpmSim* sim) {
   const size_t n = sim->count;
   const unsigned nbr = blocks_for(n, kP2gBlock);
   if (sim->n_mats == 1)
-    p2g_sched_kernel<MODEL, O, EXACT, true><<<nbr, kP2gBlock, 0, sim->stream>>>(sim->soa[sim->cur], n, sim->mats, sim->mat0, sim->grid, sim->k,
-                                                                                sim->tm_streams[sim->cur][2]);
+    p2g_sched_kernel<MODEL, O, EXACT, true, KEYS><<<nbr, kP2gBlock, 0, sim->stream>>>(sim->soa[sim->cur], n, sim->mats, sim->mat0, sim->grid, sim->k,
+                                                                                      sim->tm_streams[sim->cur][2], sim->keys[0], sim->vals[0]);
   else
-    p2g_sched_kernel<MODEL, O, EXACT, false><<<nbr, kP2gBlock, 0, sim->stream>>>(sim->soa[sim->cur], n, sim->mats, sim->mat0, sim->grid, sim->k,
-                                                                                 sim->tm_streams[sim->cur][2]);
+    p2g_sched_kernel<MODEL, O, EXACT, false, KEYS><<<nbr, kP2gBlock, 0, sim->stream>>>(sim->soa[sim->cur], n, sim->mats, sim->mat0, sim->grid, sim->k,
+                                                                                       sim->tm_streams[sim->cur][2], sim->keys[0], sim->vals[0]);
+}
+template <int MODEL, class O, bool EXACT>
+void launch_p2g_sched(MpmSim* sim, bool keys) {
+  if (keys) launch_p2g_sched_k<MODEL, O, EXACT, true>(sim); else launch_p2g_sched_k<MODEL, O, EXACT, false>(sim);
 }
 
+// keys: also write the cell keys of the re-bin that follows in this substep; *keys_done says whether that happened
 template <int MODEL>
-int launch_p2g(MpmSim* sim) {
+int launch_p2g(MpmSim* sim, bool keys, bool* keys_done) {
   const size_t n = sim->count;
   Soa& p = sim->soa[sim->cur];
+  *keys_done = false;
   if (sim->par.p2g_mode == MPM_P2G_RUNS && sim->k.N + kKeyBias <= 1023) {
-    if (sim->par.svd_mode == MPM_SVD_EXACT) launch_p2g_sched<MODEL, ExactOps, true>(sim); else launch_p2g_sched<MODEL, FastOps, false>(sim);
+    if (sim->par.svd_mode == MPM_SVD_EXACT) launch_p2g_sched<MODEL, ExactOps, true>(sim, keys); else launch_p2g_sched<MODEL, FastOps, false>(sim, keys);
+    *keys_done = keys;
     return 0;
   }
   const unsigned nb = blocks_for(n, kParticleBlock);
@@ -354,10 +365,13 @@ int launch_p2g(MpmSim* sim) {
     p2g_kernel<MODEL, FastOps, false><<<nb, kParticleBlock, 0, sim->stream>>>(p, n, sim->mats, sim->grid, sim->k);
   return 0;
 }
-int do_p2g(MpmSim* sim) {
+int do_p2g(MpmSim* sim, bool keys = false, bool* keys_done = nullptr) {
   StageTimer tm(sim, MPM_STAGE_P2G);
+  bool done = false;
+  if (keys_done) *keys_done = false;
   if (sim->count == 0) return 0;
-  if (sim->par.model == MPM_MODEL_SNOW) launch_p2g<MPM_MODEL_SNOW>(sim); else launch_p2g<MPM_MODEL_FIXED_COROTATED>(sim);
+  if (sim->par.model == MPM_MODEL_SNOW) launch_p2g<MPM_MODEL_SNOW>(sim, keys, &done); else launch_p2g<MPM_MODEL_FIXED_COROTATED>(sim, keys, &done);
+  if (keys_done) *keys_done = done;
   sim->launches++;
   CK(cudaGetLastError());
   return 0;
@@ -385,7 +399,8 @@ void launch_g2p_tile_impl(MpmSim* sim) {
   const unsigned ctas = (unsigned)std::min<size_t>(max_tiles, (size_t)sim->n_sms * per_sm);
   g2p_tile_kernel<MODEL, O, LT, COUNT_MOVED><<<ctas, kG2pThreads, smem, sim->stream>>>(
       sim->soa[sim->cur], sim->mats, sim->grid, sim->k, sim->tiles, sim->d_n_tiles, sim->tm_grid[LT == kLtSmall ? 0 : 1],
-      sim->tm_streams[sim->cur][MODEL == MPM_MODEL_SNOW ? 1 : 0], sim->d_moved, sim->count);
+      sim->tm_streams[sim->cur][MODEL == MPM_MODEL_SNOW ? 1 : 0], sim->d_moved, sim->count, sim->d_tile_counters, sim->tile_parity);
+  sim->tile_parity ^= 1;
 }
 template <int MODEL, class O, int LT>
 void launch_g2p_tile(MpmSim* sim) {  // the cell-crossing count costs a register the default path cannot spare
@@ -580,6 +595,8 @@ int mpm_create(const MpmParams* params, const MpmMaterial* materials, int n_mate
   CKC(cudaMalloc(&sim->d_span, 2 * sizeof(unsigned int)));
   CKC(cudaMallocHost(&sim->h_span, 2 * sizeof(unsigned int)));
   CKC(cudaEventCreateWithFlags(&sim->span_ev, cudaEventDisableTiming));
+  CKC(cudaMalloc(&sim->d_tile_counters, 2 * sizeof(unsigned int)));
+  CKC(cudaMemsetAsync(sim->d_tile_counters, 0, 2 * sizeof(unsigned int), sim->stream));
   CKC(cudaMalloc(&sim->d_moved, sizeof(unsigned long long)));
   CKC(cudaMemsetAsync(sim->d_moved, 0, sizeof(unsigned long long), sim->stream));
   CKC(cudaMallocHost(&sim->h_moved, sizeof(unsigned long long)));
@@ -619,6 +636,7 @@ void mpm_destroy(MpmSim* sim) {
   cudaFree(sim->tile_base);
   cudaFree(sim->d_n_tiles);
   cudaFree(sim->d_moved);
+  cudaFree(sim->d_tile_counters);
   if (sim->h_moved) cudaFreeHost(sim->h_moved);
   if (sim->moved_ev) cudaEventDestroy(sim->moved_ev);
   if (sim->h_span) cudaFreeHost(sim->h_span);
@@ -802,14 +820,15 @@ int mpm_advance(MpmSim* sim, int n_substeps) {
       if (int rc = do_grid(sim)) return rc;
       sim->grid_ready = true;
     } else {
+      bool keys_ready = false;  // slab handles tombstone leavers at the re-bin, which changes their keys
       if (int rc = do_reset(sim)) return rc;
-      if (int rc = do_p2g(sim)) return rc;
+      if (int rc = do_p2g(sim, rebin_late && !sim->comm.active(), &keys_ready)) return rc;
       if (int rc = do_exchange(sim)) return rc;
       if (int rc = do_grid(sim)) return rc;
       // a due re-bin runs here when it can: G2P is about to overwrite v and C, so only x, F, Jp
       // have to move (the keys come from the positions this substep started with)
       if (rebin_late) {
-        if (int rc = do_sort(sim, true)) return rc;
+        if (int rc = do_sort(sim, true, keys_ready)) return rc;
       }
       if (int rc = do_g2p(sim)) return rc;
       if (adaptive && !sim->moved_pending) {

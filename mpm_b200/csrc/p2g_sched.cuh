@@ -269,10 +269,13 @@ __device__ __forceinline__ void p2g_list_and_scatter_runs(P2gSmem& sm, uint32_t 
   p2g_scatter_runs(sm, n_runs, tid, grid, k);
 }
 
-template <int MODEL, class O, bool EXACT, bool ONE_MAT>
+// KEYS: also emit the cell keys (and the identity permutation) of a re-bin that follows in the same
+// substep — the positions are in registers here anyway, which saves the sort its own pass over them
+// (cell_key_kernel, sort.cuh; same key: clamped base node, x local to the slab, z fastest).
+template <int MODEL, class O, bool EXACT, bool ONE_MAT, bool KEYS>
 __global__ void __launch_bounds__(kP2gBlock, MPM_P2G_MINBLK)
 p2g_sched_kernel(Soa p, size_t count, const MpmMaterial* __restrict__ mats, const MpmMaterial mat0, float4* __restrict__ grid,
-                 KParams k, const __grid_constant__ CUtensorMap tm_streams) {
+                 KParams k, const __grid_constant__ CUtensorMap tm_streams, uint32_t* __restrict__ sort_keys, uint32_t* __restrict__ sort_vals) {
   __shared__ P2gSmem sm;
   const int tid = threadIdx.x;
   const size_t pi = (size_t)blockIdx.x * kP2gBlock + tid;
@@ -317,6 +320,14 @@ p2g_sched_kernel(Soa p, size_t count, const MpmMaterial* __restrict__ mats, cons
       }
     const float Jp = (MODEL == MPM_MODEL_SNOW) ? MPM_P2G_IN(SJ) : 1.0f;  // fixed-corotated never changes Jp
 #undef MPM_P2G_IN
+    if (KEYS) {
+      int b[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) b[a] = min(max((int)(x[a] * k.dx_inv - 0.5f), 0), k.N - 1);
+      const int bx = min(max(b[0] - k.x0, 0), k.nxl - 1);
+      sort_keys[pi] = (uint32_t)((bx * k.N + b[1]) * k.N + b[2]);
+      sort_vals[pi] = (uint32_t)pi;
+    }
     MpmMaterial m;
     if constexpr (ONE_MAT) m = mat0; else m = load_material(mats, p.mat[pi]);  // ONE_MAT: operands straight from the constant bank
     const P2gPayload o = p2g_prepare<MODEL, O, EXACT>(x, v, F, C, Jp, m, k);

@@ -42,6 +42,30 @@ def test_sort_bit_exact(count):
     assert back.tobytes() == p.tobytes()  # upload -> sort -> download restores upload order bit for bit
 
 
+def test_rebin_inside_a_substep_uses_keys_from_p2g():
+    """A due re-bin runs between the grid update and G2P with the cell keys written by that substep's
+    P2G kernel (positions at the start of the substep): keys sorted, each key = the oracle's key of
+    the particle in that slot, and the state still matches the oracle afterwards."""
+    N = 32
+    p, mats = scenes.two_spheres(N, kind=ol.SNOW, perturb=False)
+    p["v"][:, 0] += 4.0
+    sim = _sim(N, mats, ol.SNOW, 0, sort_every=3)
+    sim.upload(p)
+    sim.advance(3)
+    before = sim.download()          # positions the 4th substep starts with
+    r0 = sim.rebins
+    sim.advance(1)                   # re-bin due: happens inside this substep
+    assert sim.rebins == r0 + 1
+    keys, ids = sim.sort_state()
+    ko = ol.cell_keys(before, DT, N)
+    assert (np.diff(keys.astype(np.int64)) >= 0).all()
+    assert np.array_equal(keys, ko[ids])
+    assert (ko != ol.cell_keys(p, DT, N)).sum() > 100   # the scene did change cells since the upload
+    ref, _ = ol.advance(p.copy(), mats, DT, N, ol.SNOW, 4)
+    got = sim.download()
+    assert np.abs(got["x"].astype(np.float64) - ref["x"]).max() * N < 1e-4
+
+
 def test_dense_block_generator_matches_host():
     import mpm_b200
 
