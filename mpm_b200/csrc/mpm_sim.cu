@@ -97,6 +97,7 @@ struct MpmSim {
   unsigned long long* h_moved = nullptr;  // pinned
   cudaEvent_t moved_ev = nullptr;
   bool moved_pending = false;
+  uint64_t moved_issued_at = 0;
   unsigned long long moved_seen = 0;
   uint64_t rebins = 0;
 
@@ -788,7 +789,10 @@ int mpm_advance(MpmSim* sim, int n_substeps) {
     if (adaptive) {
       // re-bin on measured disorder: the count of cell crossings since the last re-bin arrives a
       // substep or two late (asynchronous read-back), which is early enough for a locality heuristic
-      if (sim->moved_pending && cudaEventQuery(sim->moved_ev) == cudaSuccess) {
+      // (the host may enqueue substeps far ahead of the device: a read-back older than 4 substeps is
+      // waited for, which also bounds that run-ahead)
+      if (sim->moved_pending && (sim->substeps - sim->moved_issued_at >= 4 || cudaEventQuery(sim->moved_ev) == cudaSuccess)) {
+        CK(cudaEventSynchronize(sim->moved_ev));
         sim->moved_pending = false;
         sim->moved_seen = *sim->h_moved;
       }
@@ -835,6 +839,7 @@ int mpm_advance(MpmSim* sim, int n_substeps) {
         CK(cudaMemcpyAsync(sim->h_moved, sim->d_moved, sizeof(unsigned long long), cudaMemcpyDeviceToHost, sim->stream));
         CK(cudaEventRecord(sim->moved_ev, sim->stream));
         sim->moved_pending = true;
+        sim->moved_issued_at = sim->substeps;
       }
     }
     sim->t += (double)sim->par.dt;

@@ -47,10 +47,19 @@ radix_hist_kernel(const uint32_t* __restrict__ keys, size_t count, int shift, ui
   for (int d = threadIdx.x; d < kRadix; d += kSortThreads) h[d] = 0;
   __syncthreads();
   const size_t tile0 = (size_t)blockIdx.x * kSortTile;
+  static_assert(kSortItems == 8, "two 16-byte loads per thread");
+  // the histogram does not care which thread counts which key of the tile: thread t takes the 8
+  // consecutive keys at tile0 + 8 t with two independent 16-byte loads issued before any is used
+  // (one 4-byte load feeding one atomic at a time left the kernel at 2 TB/s, latency-bound)
+  const size_t i0 = tile0 + (size_t)threadIdx.x * kSortItems;
+  if (i0 + kSortItems <= count) {
+    const uint4 a = *reinterpret_cast<const uint4*>(keys + i0);
+    const uint4 b = *reinterpret_cast<const uint4*>(keys + i0 + 4);
+    const uint32_t kk[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-  for (int it = 0; it < kSortItems; ++it) {
-    const size_t i = tile0 + (size_t)it * kSortThreads + threadIdx.x;
-    if (i < count) atomicAdd(&h[(keys[i] >> shift) & (kRadix - 1)], 1u);
+    for (int it = 0; it < kSortItems; ++it) atomicAdd(&h[(kk[it] >> shift) & (kRadix - 1)], 1u);
+  } else {
+    for (size_t i = i0; i < count && i < i0 + kSortItems; ++i) atomicAdd(&h[(keys[i] >> shift) & (kRadix - 1)], 1u);
   }
   __syncthreads();
   for (int d = threadIdx.x; d < kRadix; d += kSortThreads) table[(size_t)d * n_tiles + blockIdx.x] = h[d];
@@ -132,7 +141,10 @@ __global__ void __launch_bounds__(kScanThreads) scan_downsweep_kernel(uint32_t* 
 
 // (c) stable scatter.  Warp w owns the contiguous chunk [tile0 + w*256, +256) of its tile and
 // walks it 32 keys at a time, so (warp, iteration, lane) order is the input order.
-__global__ void __launch_bounds__(kSortThreads)
+#ifndef MPM_SCATTER_MINBLK
+#define MPM_SCATTER_MINBLK 5
+#endif
+__global__ void __launch_bounds__(kSortThreads, MPM_SCATTER_MINBLK)
 radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ keys_out,
                      uint32_t* __restrict__ vals_out, size_t count, int shift, const uint32_t* __restrict__ table, int n_tiles) {
   __shared__ uint32_t cnt[kSortWarps][kRadix];
@@ -140,15 +152,17 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
   for (int d = threadIdx.x; d < kSortWarps * kRadix; d += kSortThreads) (&cnt[0][0])[d] = 0;
   __syncthreads();
   const size_t chunk0 = (size_t)blockIdx.x * kSortTile + (size_t)warp * (kSortItems * 32);
-  uint32_t key[kSortItems], val[kSortItems], rank[kSortItems];
+  // Only the ranks stay in registers between the two loops; keys and values are read again for the
+  // write-out (they are in L1/L2 by then).  Holding them cost 16 registers and a third of the
+  // resident warps of a kernel that does little but wait for memory.
+  uint32_t rank[kSortItems];
   const uint32_t lt_mask = (1u << lane) - 1u;
 #pragma unroll
   for (int it = 0; it < kSortItems; ++it) {
     const size_t i = chunk0 + (size_t)it * 32 + lane;
     const bool valid = i < count;
-    key[it] = valid ? keys_in[i] : 0u;
-    val[it] = valid ? vals_in[i] : 0u;
-    const uint32_t digit = valid ? ((key[it] >> shift) & (kRadix - 1)) : (uint32_t)(kRadix + lane);
+    const uint32_t key = valid ? keys_in[i] : 0u;
+    const uint32_t digit = valid ? ((key >> shift) & (kRadix - 1)) : (uint32_t)(kRadix + lane);
     const uint32_t peers = __match_any_sync(0xffffffffu, digit);
     const int leader = __ffs(peers) - 1;
     uint32_t before = 0;
@@ -176,10 +190,11 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
   for (int it = 0; it < kSortItems; ++it) {
     const size_t i = chunk0 + (size_t)it * 32 + lane;
     if (i < count) {
-      const uint32_t digit = (key[it] >> shift) & (kRadix - 1);
+      const uint32_t key = keys_in[i];
+      const uint32_t digit = (key >> shift) & (kRadix - 1);
       const uint32_t pos = cnt[warp][digit] + rank[it];
-      keys_out[pos] = key[it];
-      vals_out[pos] = val[it];
+      keys_out[pos] = key;
+      vals_out[pos] = vals_in[i];
     }
   }
 }
