@@ -3,6 +3,7 @@
 // Accepted forms: --name value, --name=value.  A parse error prints a message and exits with
 // status 1, like the reference (options.h:48-51).  Extensions (not in the reference, all optional):
 // --steps (stop after this many substeps; the reference loops until killed), --svd exact|fast,
+// --model snow|fixed_corotated (the compile-time MaterialModel alias of include/mpm.cuh:25 as data),
 // --sort-every, --rebin-permille, --sync-every, --frame-rate.
 #pragma once
 #include <cstdint>
@@ -35,6 +36,7 @@ struct CLIOptions {
   // Extensions.
   long long steps = -1;
   std::string svd = "exact";
+  std::string model = "snow";  // which MaterialModel alias: snow = MMSnow (the reference's choice, mpm.cuh:25), fixed_corotated = MMFixedCorotated
   u32 sort_every = 8;
   u32 rebin_permille = 0;  // MpmParams.rebin_permille
   u32 sync_every = 20;  // src/main.cu:99
@@ -91,6 +93,7 @@ struct CLIOptions {
         else if (k == "laplacian_smooth") laplacian_smooth = std::stoi(v);
         else if (k == "steps") steps = std::stoll(v);
         else if (k == "svd") svd = v;
+        else if (k == "model") model = v;
         else if (k == "sort-every") sort_every = to_u32(v);
         else if (k == "rebin-permille") rebin_permille = to_u32(v);
         else if (k == "sync-every") sync_every = to_u32(v);
@@ -105,7 +108,7 @@ struct CLIOptions {
       err = "Argument could not be parsed";
       return false;
     }
-    if (N == 0 || (svd != "exact" && svd != "fast")) {
+    if (N == 0 || (svd != "exact" && svd != "fast") || (model != "snow" && model != "fixed_corotated")) {
       err = "Argument out of range";
       return false;
     }

@@ -126,7 +126,7 @@ class Simulation {
     MpmParams p{};
     p.dt = par.dt;
     p.N = par.N;
-    p.model = MPM_MODEL_SNOW;  // mpm.cuh:25: MaterialModel = MMSnow
+    p.model = opts_.model == "fixed_corotated" ? MPM_MODEL_FIXED_COROTATED : MPM_MODEL_SNOW;  // mpm.cuh:25: MaterialModel = MMSnow
     p.svd_mode = opts_.svd == "fast" ? MPM_SVD_FAST : MPM_SVD_EXACT;
     p.sort_every = opts_.sort_every;
     p.rebin_permille = opts_.rebin_permille;

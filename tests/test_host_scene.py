@@ -22,7 +22,9 @@ def test_options_defaults_forms_and_errors():
     host.lib()  # builds the CLI too
     s = host.Scene("--scene", os.path.join(SCENES, "rubber_duck.toml"), "--N=16", "--particle-count", "10000")
     assert s.n_objects == 2 and len(s.materials) == 1
-    for bad in (["--bogus", "1"], ["--N"], ["--N", "abc"], ["--N", "-4"], ["positional"]):
+    host.Scene("--scene", os.path.join(SCENES, "rubber_duck.toml"), "--N", "16", "--particle-count", "2000", "--model", "fixed_corotated",
+               "--svd=fast", "--rebin-permille", "50", "--sort-every", "0")
+    for bad in (["--bogus", "1"], ["--N"], ["--N", "abc"], ["--N", "-4"], ["positional"], ["--model", "jelly"], ["--svd", "sloppy"]):
         r = subprocess.run([CLI] + bad, capture_output=True, text=True)
         assert r.returncode == 1 and r.stdout.strip(), bad  # message + exit(1), like options.h:48-51
     with pytest.raises(host.MpmError):
