@@ -192,3 +192,62 @@ def test_mesh_builder_and_particle_writer(tmp_path):
     assert lines[4] == f"NUMBER_OF_PARTICLES: {len(x)}" and lines[5] == "BEGIN DATA"
     data = np.array([l.split() for l in lines[6:]], np.float64)
     assert np.array_equal(data[:, 0], np.arange(len(x))) and np.array_equal(data[:, 1:4].astype(np.float32), x) and (data[:, 7].astype(np.float32) == np.float32(0.1)).all()
+
+
+def test_toml_subset_edge_cases(tmp_path):
+    """Comments, multi-line arrays, literal strings, escapes, underscores and exponents parse like
+    tomllib; constructs outside the subset are rejected instead of being misread."""
+    good = tmp_path / "good.toml"
+    good.write_text('''# leading comment
+[[material]]   # trailing comment
+name = 'lit # not a comment'
+density = 1_000   # underscore
+E = 1.4E+5
+Nu = 2e-1
+[[material]]
+name = "esc \\"quoted\\" \\\\ tab\\t"
+[[object]]
+material = 'lit # not a comment'
+mesh = "cube.obj"
+size = 0.25
+position = [
+  0.1,   # x
+  0.2,
+  0.3,
+]
+velocity = [0, -1, 0]
+''')
+    s = host.Scene("--scene", str(good), "--N", "16", "--particle-count", "4000")
+    doc = so.load_scene_toml(str(good))
+    assert doc["material"][0]["name"] == "lit # not a comment" and doc["material"][1]["name"] == 'esc "quoted" \\ tab\t'
+    mats = s.materials
+    assert len(mats) == 2 and s.n_objects == 1
+    assert np.isclose(mats[0]["particleMass"], np.float32(1000.0) * np.float32(1.0 / 4000))
+    p = s.full_particles()
+    assert (p["material_type"] == 0).all() and (p["v"] == np.float32([0, -1, 0])).all()
+    assert (p["x"] >= np.float32([0.1, 0.2, 0.3]) - 1e-6).all() and (p["x"] <= np.float32([0.35, 0.45, 0.55]) + 1e-6).all()
+    for name, text in (("table", "[material]\nname = 'x'\n"), ("dotted", "[[material]]\na.b = 1\n"), ("unterminated", "[[material]]\nname = \"x\n"),
+                       ("garbage", "[[material]]\ndensity = 7 8\n"), ("array", "[[object]]\nposition = [1, 2\n"),
+                       ("noposition", "[[material]]\nname='m'\n[[object]]\nmaterial='m'\nvelocity=[0,0,0]\n")):
+        bad = tmp_path / (name + ".toml")
+        bad.write_text(text)
+        with pytest.raises(host.MpmError):
+            host.Scene("--scene", str(bad), "--N", "16", "--particle-count", "1000")
+
+
+def test_obj_negative_indices_and_polygons(tmp_path):
+    (tmp_path / "meshes").mkdir()
+    obj = tmp_path / "meshes" / "box.obj"
+    # a cube from 6 quads, the last two faces with negative (relative) indices
+    obj.write_text("v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nv 0 0 1\nv 1 0 1\nv 1 1 1\nv 0 1 1\n"
+                   "f 1 4 3 2\nf 5 6 7 8\nf 1 2 6 5\nf 4 8 7 3\nf -8 -4 -1 -5\nf -7 -6 -2 -3\n")
+    V, F, sub = host.load_mesh(str(obj), 1.0, [0.0, 0.0, 0.0])
+    assert not sub and F.shape == (12, 3)
+    w = host.winding_numbers(V, F, np.float32([[0.5, 0.5, 0.5], [1.5, 0.5, 0.5]]))
+    assert abs(abs(w[0]) - 1) < 1e-5 and abs(w[1]) < 1e-5
+    Vs, Fs, _ = host.load_mesh("/nonexistent/meshes/cube.obj", 1.0, [0.0, 0.0, 0.0])
+    pts = np.random.default_rng(3).uniform(-0.2, 1.2, (500, 3)).astype(np.float32)
+    inside = ((pts > 0.01) & (pts < 0.99)).all(1)
+    outside = ((pts < -0.01) | (pts > 1.01)).any(1)
+    ws = host.winding_numbers(Vs, Fs, pts)
+    assert np.abs(ws[inside] - 1).max() < 1e-5 and np.abs(ws[outside]).max() < 1e-5
