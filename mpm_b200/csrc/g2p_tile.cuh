@@ -152,13 +152,14 @@ __device__ __forceinline__ void g2p_gather27(const float4* __restrict__ tp, long
 }
 
 template <int MODEL, class O, int LT, bool COUNT_MOVED>
-__device__ __forceinline__ void g2p_tile_compute(const Soa& p, const MpmMaterial* __restrict__ mats, const float4* __restrict__ grid,
+__device__ __forceinline__ void g2p_tile_compute(const Soa& p, const MpmMaterial* __restrict__ mats, const MpmMaterial& mat0, bool one_mat,
+                                                 const float4* __restrict__ grid,
                                                  const KParams& k, const TileHeader& h, const float4* __restrict__ box,
                                                  float4* __restrict__ wtile, const float* __restrict__ ps, int tid, unsigned& moved) {
   const bool live = tid < h.n;
   const size_t pi = (size_t)h.start + tid;
   uint8_t mat_id = 0;
-  if (MODEL == MPM_MODEL_SNOW && live) mat_id = p.mat[pi];
+  if (MODEL == MPM_MODEL_SNOW && live && !one_mat) mat_id = p.mat[pi];
   ps += h.off + tid;  // this particle's column of the stream box
   float x[3];
 #pragma unroll
@@ -268,7 +269,8 @@ __device__ __forceinline__ void g2p_tile_compute(const Soa& p, const MpmMaterial
   F = mul_ab(G, F);  // F <- (I + dt C) F
   if (MODEL == MPM_MODEL_SNOW) {
     float Jp = ps[SJ * kTile];
-    const MpmMaterial m = load_material(mats, mat_id);
+    // single-material handles read the clamps straight from the kernel parameters (uniform branch)
+    const MpmMaterial m = one_mat ? mat0 : load_material(mats, mat_id);
     snow_plasticity<O>(F, Jp, m);
     MPM_STP(p.s(SJ) + pi, Jp);
   }
@@ -297,7 +299,7 @@ __device__ __forceinline__ void g2p_tile_compute(const Soa& p, const MpmMaterial
 // Persistent CTAs: tile `it` of this CTA = blockIdx.x + it * gridDim.x.
 template <int MODEL, class O, int LT, bool COUNT_MOVED>
 __global__ void __launch_bounds__(kG2pThreads, MPM_G2P_SELFFEED ? 4 : MPM_G2P_TILE_MINBLK)
-g2p_tile_kernel(Soa p, const MpmMaterial* __restrict__ mats, const float4* __restrict__ grid, KParams k,
+g2p_tile_kernel(Soa p, const MpmMaterial* __restrict__ mats, const MpmMaterial mat0, const bool one_mat, const float4* __restrict__ grid, KParams k,
                 const TileDesc* __restrict__ tiles, const uint32_t* __restrict__ n_tiles_ptr,
                 const __grid_constant__ CUtensorMap tm_grid, const __grid_constant__ CUtensorMap tm_streams,
                 unsigned long long* __restrict__ moved_total, size_t count, unsigned int* __restrict__ tile_counters, int parity) {
@@ -388,7 +390,7 @@ g2p_tile_kernel(Soa p, const MpmMaterial* __restrict__ mats, const float4* __res
     mbar_wait(full + s, (uint32_t)((it / kG2pStages) & 1));
     if (MPM_G2P_DYNAMIC && hdr[s].n < 0) break;  // no more tiles for this CTA
     const unsigned char* st = smem + s * kStage;
-    g2p_tile_compute<MODEL, O, LT, COUNT_MOVED>(p, mats, grid, k, hdr[s], reinterpret_cast<const float4*>(st),
+    g2p_tile_compute<MODEL, O, LT, COUNT_MOVED>(p, mats, mat0, one_mat, grid, k, hdr[s], reinterpret_cast<const float4*>(st),
                                    bricks + (tid >> 5) * (kWarpBrickX * kWarpBrickY * kWarpBrickZ),
                                    reinterpret_cast<const float*>(st + L::box_bytes(LT)), tid, moved);
     __syncwarp();  // stage s and the warp's brick are free again

@@ -399,7 +399,7 @@ void launch_g2p_tile_impl(MpmSim* sim) {
   const size_t max_tiles = MPM_G2P_FLAT_TILES ? (sim->count + kTile - 1) / kTile : sim->count / kTileMax + sim->n_rows + 1;
   const unsigned ctas = (unsigned)std::min<size_t>(max_tiles, (size_t)sim->n_sms * per_sm);
   g2p_tile_kernel<MODEL, O, LT, COUNT_MOVED><<<ctas, kG2pThreads, smem, sim->stream>>>(
-      sim->soa[sim->cur], sim->mats, sim->grid, sim->k, sim->tiles, sim->d_n_tiles, sim->tm_grid[LT == kLtSmall ? 0 : 1],
+      sim->soa[sim->cur], sim->mats, sim->mat0, sim->n_mats == 1, sim->grid, sim->k, sim->tiles, sim->d_n_tiles, sim->tm_grid[LT == kLtSmall ? 0 : 1],
       sim->tm_streams[sim->cur][MODEL == MPM_MODEL_SNOW ? 1 : 0], sim->d_moved, sim->count, sim->d_tile_counters, sim->tile_parity);
   sim->tile_parity ^= 1;
 }
