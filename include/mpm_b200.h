@@ -88,7 +88,9 @@ typedef struct MpmParams {
   uint32_t fuse_mode;   /* MPM_FUSE_* */
   uint32_t rebin_permille; /* 0 = fixed cadence only.  > 0: also re-bin as soon as the cell crossings counted by G2P
                            since the last re-bin exceed this many per mille of the particle count (needs
-                           G2P_TILE, separate kernels); sort_every = 0 then means "only on demand" */
+                           G2P_TILE, separate kernels, a single-device handle — slab handles keep the fixed
+                           cadence, their ranks must re-bin in the same substep); sort_every = 0 then means
+                           "only on demand" */
   uint32_t reserved_;   /* must be 0 */
 } MpmParams;
 

@@ -785,7 +785,8 @@ int mpm_advance(MpmSim* sim, int n_substeps) {
   for (int s = 0; s < n_substeps; ++s) {
     bool rebin_late = false;
     bool due = sim->par.sort_every && sim->steps_since_sort >= sim->par.sort_every;
-    const bool adaptive = sim->par.rebin_permille && !sim->fused && sim->par.g2p_mode == MPM_G2P_TILE;
+    // (not for slab handles: every rank must reach the migration of a re-bin in the same substep)
+    const bool adaptive = sim->par.rebin_permille && !sim->fused && sim->par.g2p_mode == MPM_G2P_TILE && !sim->comm.active();
     if (adaptive) {
       // re-bin on measured disorder: the count of cell crossings since the last re-bin arrives a
       // substep or two late (asynchronous read-back), which is early enough for a locality heuristic
