@@ -29,11 +29,10 @@ P_PER_GPU = 1 << 26
 BYTES_PER_PARTICLE = 252   # P2G read 100 + G2P read 52 + G2P write 100
 BYTES_PER_NODE = 80        # zero 16 + P2G write-back 16 + grid update 16+16 + G2P read 16
 # per-kernel algorithmic bytes (DESIGN.md "Kernels"): (bytes per particle, bytes per node)
-# g2p2g = G2P of one substep + P2G of the next in one kernel: it does the work of both, so its
-# algorithmic bytes are the sum (252 B/particle); what it really has to move is
-# 152 B/particle + 32 B/node because the P2G inputs never leave the registers (reported beside it)
-KERNEL_BYTES = {"reset": (0, 16), "p2g": (100, 16), "grid": (0, 32), "g2p": (152, 16), "g2p2g": (252, 32)}
-FUSED_MIN_BYTES = (152, 32)
+KERNEL_BYTES = {"reset": (0, 16), "p2g": (100, 16), "grid": (0, 32), "g2p": (152, 16)}
+# what the kernels of the hand-over pipeline actually have to move: P2G reads v, A, x
+# (60 B), G2P reads x, F (, Jp) and writes 24 (25) streams; reported beside the SURVEY formula
+MOVED_BYTES = {"reset": (0, 16), "p2g": (60, 16), "grid": (0, 32), "g2p": (144, 16)}
 E2E_SUBSTEPS_PER_SYNC = 20  # the reference main loop calls syncDevice every 20 advances (src/main.cu:99)
 
 
@@ -188,7 +187,9 @@ def main():
     ap.add_argument("--particles", type=int, default=P_PER_GPU, help="particles per GPU (default 2^26)")
     ap.add_argument("--g2p", default="tile", choices=["tile", "direct"], help="G2P kernel (MpmParams.g2p_mode)")
     ap.add_argument("--p2g", default="runs", choices=["runs", "direct"], help="P2G kernel (MpmParams.p2g_mode)")
-    ap.add_argument("--fuse", default="off", choices=["g2p2g", "off"], help="substep pipeline (MpmParams.fuse_mode)")
+    ap.add_argument("--pipeline", default="handover", choices=["handover", "classic"], help="substep pipeline (MpmParams.pipeline)")
+    ap.add_argument("--shear", type=float, default=0.0, help="stressed block: shear velocity field [1/s] (mpm_generate_dense_block_stressed)")
+    ap.add_argument("--f-noise", type=float, default=0.0, help="stressed block: amplitude of the perturbation of F")
     ap.add_argument("--rebin-permille", type=int, default=0,
                     help="MpmParams.rebin_permille: also re-bin on measured disorder (0 = fixed cadence only, the default)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
@@ -240,13 +241,13 @@ def main():
                        x_begin=xb, x_end=xe, device=local_rank, capacity=cap,
                        p2g_mode=mpm_b200.P2G_RUNS if args.p2g == "runs" else mpm_b200.P2G_DIRECT,
                        g2p_mode=mpm_b200.G2P_TILE if args.g2p == "tile" else mpm_b200.G2P_DIRECT,
-                       fuse_mode=mpm_b200.FUSE_G2P2G if args.fuse == "g2p2g" else mpm_b200.FUSE_OFF,
+                       pipeline=mpm_b200.PIPE_HANDOVER if args.pipeline == "handover" else mpm_b200.PIPE_CLASSIC,
                        rebin_permille=args.rebin_permille)
     if world > 1:
         from mpm_b200 import slabs as _slabs
 
         sim.attach_comm(_slabs.share_unique_id(dist, rank, mpm_b200.comm_unique_id), rank, world)
-    sim.generate_dense_block(P_total, seed=1234)
+    sim.generate_dense_block(P_total, seed=1234, shear=args.shear, f_noise=args.f_noise)
     sim.sync()
     P_local = sim.count
     G_local = sim.grid_nodes
@@ -289,9 +290,10 @@ def main():
     n_prof = min(args.steps, 16)
     sim.advance(n_prof)
     st = sim.stage_times()
+    sim.set_stage_timing(False)
     barrier()
     peak, peak_src = peaks()
-    substep_keys = ("reset", "p2g", "grid", "g2p", "g2p2g")
+    substep_keys = ("reset", "p2g", "grid", "g2p")
     dom = max(substep_keys, key=lambda s: st[s])
     bp, bn = KERNEL_BYTES[dom]
     dom_ms = st[dom] / n_prof
@@ -299,12 +301,6 @@ def main():
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic(dom, P_local, G_local), "peak_source": peak_src, "kernel_ms": dom_ms,
                 "algorithmic_bytes_per_launch": bp * P_local + bn * G_local}
-    if dom == "g2p2g":
-        mb = FUSED_MIN_BYTES[0] * P_local + FUSED_MIN_BYTES[1] * G_local
-        roofline["fused_min_bytes_per_launch"] = mb
-        roofline["achieved_on_fused_min_bytes"] = mb / (dom_ms * 1e-3) / 1e9
-        roofline["note"] = ("achieved = SURVEY 8(d) bytes of the two stages the kernel replaces (252 B/particle + 32 B/node) / time; "
-                            "the fused kernel itself must move only 152 B/particle + 32 B/node")
     sub_ach = (BYTES_PER_PARTICLE * P_all + BYTES_PER_NODE * G_all) / (ms_per_step * 1e-3) / 1e9 / world
     substep_roofline = {"achieved_per_gpu": sub_ach, "peak": peak, "unit": "GB/s", "frac": sub_ach / peak,
                         "bytes": "252*P + 80*G per substep (BASELINE.md)"}
@@ -346,7 +342,7 @@ def main():
                                    + (")" if world == 1 else (f" scaled weakly to {world} GPUs: 2^26 particles and ~2^24 nodes per GPU)" if args.scaling == "weak"
                                                               else f" strong scaling: the same block cut into {world} slabs)")),
                        "N": N, "particles": int(P_all), "grid_nodes": int(G_all), "dt": dt, "model": args.model,
-                       "svd_mode": args.svd, "sort_every": args.sort_every, "rebin_permille": args.rebin_permille, "p2g": args.p2g, "g2p": args.g2p, "fuse": args.fuse, "slabs": slabs if world > 1 else None,
+                       "svd_mode": args.svd, "sort_every": args.sort_every, "rebin_permille": args.rebin_permille, "p2g": args.p2g, "g2p": args.g2p, "pipeline": args.pipeline, "shear": args.shear, "f_noise": args.f_noise, "slabs": slabs if world > 1 else None,
                        "l2": "inputs (6.7 GB particles + 268 MB grid per GPU) are far larger than the 126 MB L2; no flush"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "substep_roofline": substep_roofline, "stage_ms": stage_ms,

@@ -24,29 +24,32 @@
 extern "C" {
 #endif
 
-#define MPM_B200_ABI_VERSION 4
+#define MPM_B200_ABI_VERSION 5
 
-/* which MaterialModel alias the kernels are instantiated for (reference include/mpm.cuh:25) */
-enum { MPM_MODEL_SNOW = 0, MPM_MODEL_FIXED_COROTATED = 1 };
+/* which MaterialModel alias the kernels are instantiated for (reference include/mpm.cuh:25): the classes of
+ * include/mpm_b200/MaterialModel.cuh.  Ids >= MPM_MODEL_USER are materials compiled in through
+ * include/mpm_b200/plugin.cuh (MPM_B200_REGISTER_MATERIAL). */
+enum { MPM_MODEL_SNOW = 0, MPM_MODEL_FIXED_COROTATED = 1, MPM_MODEL_JELLY = 2, MPM_MODEL_USER = 16 };
 /* svd3 arithmetic: EXACT reproduces the reference svd3 bit for bit; FAST contracts to FMA and
  * uses the hardware rsqrt approximation (deviation reported by the tests) */
 enum { MPM_SVD_EXACT = 0, MPM_SVD_FAST = 1 };
 /* P2G kernel: RUNS pre-reduces same-cell particles in registers before the vector reductions
- * (default); DIRECT issues 27 vector reductions per particle (also used when N > 1019) */
+ * (default); DIRECT is the generic kernel over the plugin concepts, 27 vector reductions per particle
+ * (also used when N > 1019 and for user-defined transfer schemes / interpolation kernels) */
 enum { MPM_P2G_RUNS = 0, MPM_P2G_DIRECT = 1 };
-/* G2P kernel: TILE stages the grid block and the particle streams of each CTA in shared memory
- * with bulk async copies (default); DIRECT gathers the 27 nodes per particle from global memory */
+/* G2P kernel: TILE stages the particle streams of each CTA in shared memory with bulk async copies
+ * (default); DIRECT is the generic kernel over the plugin concepts */
 enum { MPM_G2P_TILE = 0, MPM_G2P_DIRECT = 1 };
-/* substep pipeline: OFF (default) runs reset -> P2G -> grid update -> G2P as separate kernels, as the
- * reference does.  G2P2G runs G2P of substep s and P2G of substep s+1 as ONE warp-specialised kernel
- * over two alternating grids, so the particle state written by G2P is never read back from HBM
- * (needs P2G_RUNS + G2P_TILE, else the separate kernels run).  Same arithmetic per particle either
- * way.  Measured slower than the separate kernels so far, hence not the default.
- * In G2P2G mode the internal grid holds the NEXT substep's velocities after mpm_advance. */
-enum { MPM_FUSE_OFF = 0, MPM_FUSE_G2P2G = 1 };
+/* substep pipeline.  HANDOVER (default): between two substeps of ONE mpm_advance call, G2P computes the
+ * affine matrix of the next P2G (stress + m C) while F, C, Jp are in its registers and stores it in place
+ * of C; that P2G then reads 15 of the 25 particle streams and does not evaluate the material.  The last
+ * G2P of every mpm_advance call stores C, so the particle state is always the reference's at the API
+ * boundary.  Same arithmetic per particle either way.  CLASSIC: every P2G evaluates the material
+ * itself, as the reference does (also what DIRECT kernels and single-substep calls get). */
+enum { MPM_PIPE_HANDOVER = 0, MPM_PIPE_CLASSIC = 1 };
 /* stage indices for mpm_get_stage_times */
 enum { MPM_STAGE_SORT = 0, MPM_STAGE_RESET = 1, MPM_STAGE_P2G = 2, MPM_STAGE_GRID = 3, MPM_STAGE_G2P = 4,
-       MPM_STAGE_EXCHANGE = 5, MPM_STAGE_G2P2G = 6, MPM_STAGE_COUNT = 7 };
+       MPM_STAGE_EXCHANGE = 5, MPM_STAGE_COUNT = 6 };
 
 /* replaces the reference's 104-byte particle record at the boundary */
 typedef struct MpmParticle {
@@ -85,10 +88,10 @@ typedef struct MpmParams {
   uint32_t ghost;       /* slab handles: extra ghost x-planes either side, i.e. how many cells a particle
                            may drift out of its slab between re-bins (0 = default: 1 for slabs) */
   uint32_t g2p_mode;    /* MPM_G2P_* */
-  uint32_t fuse_mode;   /* MPM_FUSE_* */
+  uint32_t pipeline;    /* MPM_PIPE_* */
   uint32_t rebin_permille; /* 0 = fixed cadence only.  > 0: also re-bin as soon as the cell crossings counted by G2P
                            since the last re-bin exceed this many per mille of the particle count (needs
-                           G2P_TILE, separate kernels, a single-device handle — slab handles keep the fixed
+                           G2P_TILE, a single-device handle — slab handles keep the fixed
                            cadence, their ranks must re-bin in the same substep); sort_every = 0 then means
                            "only on demand" */
   uint32_t reserved_;   /* must be 0 */
@@ -103,6 +106,10 @@ void mpm_make_material(double volume, double density, double E, double Nu, doubl
 
 /* Simulation::Simulation + initCuda() minus the particle upload (src/mpm.cu:180-207) */
 int mpm_create(const MpmParams* params, const MpmMaterial* materials, int n_materials, MpmSim** out);
+/* the same for materials of any registered model: `materials` = n_materials trivially copyable objects
+ * of the model's own type, material_bytes each — what the reference memcpy's to the device
+ * (src/mpm.cu:198-201).  mpm_create is this with the 7-float MpmMaterial records converted. */
+int mpm_create_raw(const MpmParams* params, const void* materials, size_t material_bytes, int n_materials, MpmSim** out);
 /* Simulation::~Simulation (src/mpm.cu:190-195) */
 void mpm_destroy(MpmSim* sim);
 const char* mpm_last_error(const MpmSim* sim); /* sim may be NULL: last creation error */
@@ -131,6 +138,10 @@ int mpm_download_positions_async(MpmSim* sim, float* xyz, size_t capacity, size_
  * only particles whose base node lies in this handle's slab are kept */
 int mpm_generate_dense_block(MpmSim* sim, uint64_t first_id, uint64_t count, uint32_t seed, float lo, float hi,
                              uint8_t material);
+/* the same block under stress (bench.py --stress): v = shear * (y - 0.5, 0, 0.3 (x - 0.5)) and
+ * F = I + f_noise * u, u uniform in [-1, 1) from the same counter hash */
+int mpm_generate_dense_block_stressed(MpmSim* sim, uint64_t first_id, uint64_t count, uint32_t seed, float lo, float hi,
+                                      uint8_t material, float shear, float f_noise);
 size_t mpm_particle_count(const MpmSim* sim);
 
 /* Simulation::advance() x n_substeps (src/mpm.cu:323-329); asynchronous like the reference */
@@ -158,8 +169,20 @@ int mpm_debug_overwrite_particles_aos(MpmSim* sim, const MpmParticle* particles,
 int mpm_debug_download_sort(MpmSim* sim, uint32_t* keys, uint32_t* ids, size_t capacity); /* current order */
 size_t mpm_grid_nodes(const MpmSim* sim);
 
-/* accumulated CUDA-event time per stage since the last call (ms); enables timing on first call */
+/* accumulated CUDA-event time per stage since the last call (ms).  The first call switches the per-stage
+ * timing on (events + a host synchronisation around every stage: for profiling, not for production);
+ * mpm_set_stage_timing(sim, 0) switches it off again */
 int mpm_get_stage_times(MpmSim* sim, float ms[MPM_STAGE_COUNT]);
+int mpm_set_stage_timing(MpmSim* sim, int on);
+/* counters kept by the kernels (NaN / out-of-domain detection; ADVICE r1: slab escapes) */
+typedef struct MpmDiagnostics {
+  uint32_t jp_not_one;    /* 1 if any uploaded particle had Jp != 1 (fixed-corotated handles then read the Jp stream) */
+  uint32_t escaped;       /* slab handles: particle-substeps whose stencil left the planes held locally (mass was lost);
+                             a re-bin that finds this non-zero fails */
+  uint32_t nonfinite;     /* particles with a non-finite position at the last re-bin */
+  uint32_t out_of_domain; /* particles whose stencil lay wholly outside the domain at the last re-bin (frozen, like the reference) */
+} MpmDiagnostics;
+int mpm_get_diagnostics(MpmSim* sim, MpmDiagnostics* out); /* blocking */
 /* stream the handle launches on (cudaStream_t), for callers that time with their own events */
 void* mpm_stream(MpmSim* sim);
 
@@ -172,6 +195,9 @@ int mpm_attach_comm(MpmSim* sim, const void* id128, int rank, int nranks);
 int mpm_svd3_batch(const float* A, float* U, float* S, float* V, size_t n, int svd_mode);
 int mpm_polar_batch(const float* A, float* R, size_t n, int svd_mode);
 int mpm_determinant_batch(const float* A, float* det, size_t n);
+/* D^-1 of the quadratic kernel through the generic D_inv (sum_nodes w d d^T, inverted) at n positions;
+ * must equal 4 dx^-2 I (reference include/InterpolationKernel.cuh:21-50 vs :71-73) */
+int mpm_dinv_batch(const float* xyz, float* Dinv9, size_t n, uint32_t N);
 
 #ifdef __cplusplus
 }

@@ -1,17 +1,24 @@
-// 3x3 SVD / polar decomposition / determinant for the MLS-MPM substep (sm_100a).
+// mpm_b200 plugin surface — 3x3 linear algebra for material models (sm_100a).
 //
-// Replaces the reference's include/svd3_cuda.h:35-1043 (McAdams et al. TR1690) and the wrappers
-// of src/linalg.cu:18-53.  Written from the algorithm, not from the reference's text: the Jacobi
-// conjugation and the QR Givens step are one routine each, applied with rotated roles.
+// Replaces the reference's include/linalg.h + src/linalg.cu:18-53 (polar_decomposition_device,
+// svd_decomposition, determinant) and include/svd3_cuda.h:35-1043 (McAdams et al. TR1690).  Written
+// from the algorithm, not from the reference's text: the Jacobi conjugation and the QR Givens step
+// are one routine each, applied with rotated roles.
 //
-// Two arithmetic policies:
-//   ExactOps — every product and sum individually rounded (__fmul_rn/__fadd_rn/__fsub_rn) and
+// Two arithmetic policies, selected per handle by MpmParams.svd_mode and passed to the material
+// templates as their second parameter:
+//   mpm::ExactOps — every product and sum individually rounded (__fmul_rn/__fadd_rn/__fsub_rn) and
 //              the correctly rounded __frsqrt_rn, i.e. exactly the operation sequence of the
 //              reference header.  Bit-identical to the reference svd3 (tests/test_gpu_linalg.py).
-//   FastOps  — plain operators (nvcc contracts to FFMA) and the MUFU.RSQ approximation.  Its
-//              deviation from ExactOps is a reported test result (<= a few 1e-7 on U, V).
+//   mpm::FastOps  — plain operators (nvcc contracts to FFMA) and the MUFU.RSQ approximation; the polar
+//              rotation comes from a Newton iteration.  Its deviation from ExactOps is a reported
+//              test result (<= a few 1e-7 on U, V).
+// The reference names live in namespace linalg, templated on the policy (default: ExactOps, the
+// reference's arithmetic).
 #pragma once
 #include <cuda_runtime.h>
+
+#include "types.cuh"
 
 namespace mpm {
 
@@ -30,9 +37,7 @@ struct FastOps {
   static __device__ __forceinline__ float rsqrt(float x) { return rsqrtf(x); }
 };
 
-struct Mat3 {
-  float m[3][3];  // row-major m[r][c]
-};
+using Mat3 = ::Mat;  // row-major m[r][c] (include/mpm_b200/types.cuh)
 
 namespace svd_detail {
 
@@ -313,30 +318,9 @@ __device__ __forceinline__ void svd3(const Mat3& Ain, Mat3& U, float S[3], Mat3&
   S[2] = a[2][2];
 }
 
-// 3x3 determinant, cofactor expansion along the first row (reference src/linalg.cu:47-52).
-__device__ __forceinline__ float det3(const Mat3& M) {
-  const float sub1 = M.m[1][0] * M.m[2][1] - M.m[1][1] * M.m[2][0];
-  const float sub2 = M.m[1][0] * M.m[2][2] - M.m[1][2] * M.m[2][0];
-  const float sub3 = M.m[1][1] * M.m[2][2] - M.m[1][2] * M.m[2][1];
-  return M.m[0][0] * sub3 - M.m[0][1] * sub2 + M.m[0][2] * sub1;
-}
-
-__device__ __forceinline__ Mat3 mul_abt(const Mat3& A, const Mat3& B) {  // A * B^T
-  Mat3 R;
-#pragma unroll
-  for (int i = 0; i < 3; ++i)
-#pragma unroll
-    for (int j = 0; j < 3; ++j) R.m[i][j] = A.m[i][0] * B.m[j][0] + A.m[i][1] * B.m[j][1] + A.m[i][2] * B.m[j][2];
-  return R;
-}
-__device__ __forceinline__ Mat3 mul_ab(const Mat3& A, const Mat3& B) {
-  Mat3 R;
-#pragma unroll
-  for (int i = 0; i < 3; ++i)
-#pragma unroll
-    for (int j = 0; j < 3; ++j) R.m[i][j] = A.m[i][0] * B.m[0][j] + A.m[i][1] * B.m[1][j] + A.m[i][2] * B.m[2][j];
-  return R;
-}
+__device__ __forceinline__ float det3(const Mat3& M) { return M.determinant(); }  // src/linalg.cu:47-52
+using ::mul_abt;
+__device__ __forceinline__ Mat3 mul_ab(const Mat3& A, const Mat3& B) { return A * B; }
 
 // Rotation factor of the polar decomposition A = R S (reference src/linalg.cu:18-33: R = U V^T).
 template <class O>
@@ -409,3 +393,40 @@ __device__ __forceinline__ Mat3 polar_rotation_newton(const Mat3& A) {
 }
 
 }  // namespace mpm
+
+// ---- the reference's names (include/linalg.h:7-12) ----------------------------------------------
+namespace linalg {
+
+// A = R S, R = U V^T, S = V Sigma V^T (src/linalg.cu:18-33)
+template <class Ops = mpm::ExactOps>
+__device__ __forceinline__ void polar_decomposition_device(const Mat& A, Mat& R, Mat& S) {
+  Mat U, V;
+  float sig[3];
+  mpm::svd3<Ops>(A, U, sig, V);
+  R = mul_abt(U, V);
+  Mat VS;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) VS.m[i][j] = V.m[i][j] * sig[j];
+  S = mul_abt(VS, V);
+}
+// rotation factor only: what the material models use (S is dead in every caller of the reference)
+template <class Ops = mpm::ExactOps>
+__device__ __forceinline__ Mat polar_rotation(const Mat& A) {
+  if constexpr (Ops::kExact) return mpm::polar_rotation<Ops>(A);
+  else return mpm::polar_rotation_newton(A);
+}
+// A = U S V^T with S diagonal (src/linalg.cu:35-45)
+template <class Ops = mpm::ExactOps>
+__device__ __forceinline__ void svd_decomposition(const Mat& A, Mat& U, Mat& S, Mat& V) {
+  float sig[3];
+  mpm::svd3<Ops>(A, U, sig, V);
+  S = Mat::Zero();
+  S.m[0][0] = sig[0];
+  S.m[1][1] = sig[1];
+  S.m[2][2] = sig[2];
+}
+__device__ __forceinline__ real determinant(const Mat& M) { return M.determinant(); }  // src/linalg.cu:47-53
+
+}  // namespace linalg

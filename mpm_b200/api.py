@@ -6,12 +6,12 @@ import numpy as np
 
 from . import build as _build
 
-SNOW, FIXED_COROTATED = 0, 1
+SNOW, FIXED_COROTATED, JELLY, MODEL_USER = 0, 1, 2, 16
 SVD_EXACT, SVD_FAST = 0, 1
 P2G_RUNS, P2G_DIRECT = 0, 1
 G2P_TILE, G2P_DIRECT = 0, 1
-FUSE_OFF, FUSE_G2P2G = 0, 1
-STAGES = ("sort", "reset", "p2g", "grid", "g2p", "exchange", "g2p2g")
+PIPE_HANDOVER, PIPE_CLASSIC = 0, 1
+STAGES = ("sort", "reset", "p2g", "grid", "g2p", "exchange")
 
 # MpmParticle == the reference's MLS_APIC_Particle (104 bytes, matrices column-major)
 PARTICLE_DTYPE = np.dtype(
@@ -27,7 +27,7 @@ class MpmParams(ctypes.Structure):
                 ("svd_mode", ctypes.c_uint32), ("sort_every", ctypes.c_uint32), ("x_begin", ctypes.c_uint32),
                 ("x_end", ctypes.c_uint32), ("device", ctypes.c_int32), ("capacity", ctypes.c_uint64),
                 ("p2g_mode", ctypes.c_uint32), ("ghost", ctypes.c_uint32), ("g2p_mode", ctypes.c_uint32),
-                ("fuse_mode", ctypes.c_uint32), ("rebin_permille", ctypes.c_uint32),
+                ("pipeline", ctypes.c_uint32), ("rebin_permille", ctypes.c_uint32),
                 ("reserved_", ctypes.c_uint32)]
 
 
@@ -67,6 +67,12 @@ def lib():
         L.mpm_make_material.restype = None
         L.mpm_make_material.argtypes = [ctypes.c_double] * 7 + [_vp]
         L.mpm_create.argtypes = [ctypes.POINTER(MpmParams), _vp, ctypes.c_int, ctypes.POINTER(_vp)]
+        L.mpm_create_raw.argtypes = [ctypes.POINTER(MpmParams), _vp, ctypes.c_size_t, ctypes.c_int, ctypes.POINTER(_vp)]
+        L.mpm_generate_dense_block_stressed.argtypes = [_vp, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_float,
+                                                        ctypes.c_float, ctypes.c_uint8, ctypes.c_float, ctypes.c_float]
+        L.mpm_set_stage_timing.argtypes = [_vp, ctypes.c_int]
+        L.mpm_get_diagnostics.argtypes = [_vp, _vp]
+        L.mpm_dinv_batch.argtypes = [_vp, _vp, ctypes.c_size_t, ctypes.c_uint32]
         L.mpm_upload_particles_aos.argtypes = [_vp, _vp, ctypes.c_size_t]
         L.mpm_append_particles_aos.argtypes = [_vp, _vp, ctypes.c_size_t]
         L.mpm_upload_particles_with_ids.argtypes = [_vp, _vp, _vp, ctypes.c_size_t]
@@ -109,11 +115,20 @@ class Sim:
     """One handle = one device.  Mirrors the device half of the reference's Simulation class."""
 
     def __init__(self, N, dt, materials, model=SNOW, svd_mode=SVD_EXACT, sort_every=0, x_begin=0, x_end=0,
-                 device=-1, capacity=0, p2g_mode=P2G_RUNS, ghost=0, g2p_mode=G2P_TILE, fuse_mode=FUSE_OFF, rebin_permille=0):
+                 device=-1, capacity=0, p2g_mode=P2G_RUNS, ghost=0, g2p_mode=G2P_TILE, pipeline=PIPE_HANDOVER, rebin_permille=0,
+                 raw_materials=None):
+        """materials: n x 7 floats (MpmMaterial = MMSnow's fields; the leading fields are used by the
+        other shipped models).  raw_materials: bytes of n objects of a registered model's own
+        material type instead (mpm_create_raw, user-defined materials)."""
         self._h = _vp()
-        mats = np.ascontiguousarray(materials, np.float32).reshape(-1, 7)
-        self.params = MpmParams(dt, N, model, svd_mode, sort_every, x_begin, x_end, device, capacity, p2g_mode, ghost, g2p_mode, fuse_mode, rebin_permille, 0)
-        rc = lib().mpm_create(ctypes.byref(self.params), _ptr(mats), mats.shape[0], ctypes.byref(self._h))
+        self.params = MpmParams(dt, N, model, svd_mode, sort_every, x_begin, x_end, device, capacity, p2g_mode, ghost, g2p_mode, pipeline, rebin_permille, 0)
+        if raw_materials is not None:
+            raw, n = raw_materials
+            buf = ctypes.create_string_buffer(bytes(raw), len(raw))
+            rc = lib().mpm_create_raw(ctypes.byref(self.params), buf, len(raw) // n, n, ctypes.byref(self._h))
+        else:
+            mats = np.ascontiguousarray(materials, np.float32).reshape(-1, 7)
+            rc = lib().mpm_create(ctypes.byref(self.params), _ptr(mats), mats.shape[0], ctypes.byref(self._h))
         if rc:
             raise MpmError(lib().mpm_last_error(None).decode())
         self.N = N
@@ -182,8 +197,8 @@ class Sim:
         self._ck(lib().mpm_download_positions_async(self._h, _ptr(out), out.shape[0], ctypes.byref(cnt)))
         return cnt.value
 
-    def generate_dense_block(self, count, seed=1234, lo=0.1, hi=0.9, material=0, first_id=0):
-        self._ck(lib().mpm_generate_dense_block(self._h, first_id, count, seed, lo, hi, material))
+    def generate_dense_block(self, count, seed=1234, lo=0.1, hi=0.9, material=0, first_id=0, shear=0.0, f_noise=0.0):
+        self._ck(lib().mpm_generate_dense_block_stressed(self._h, first_id, count, seed, lo, hi, material, shear, f_noise))
 
     @property
     def count(self):
@@ -240,6 +255,14 @@ class Sim:
         self._ck(lib().mpm_get_stage_times(self._h, _ptr(ms)))
         return dict(zip(STAGES, ms.tolist()))
 
+    def set_stage_timing(self, on):
+        self._ck(lib().mpm_set_stage_timing(self._h, 1 if on else 0))
+
+    def diagnostics(self):
+        d = np.zeros(4, np.uint32)
+        self._ck(lib().mpm_get_diagnostics(self._h, _ptr(d)))
+        return dict(zip(("jp_not_one", "escaped", "nonfinite", "out_of_domain"), (int(v) for v in d)))
+
     def attach_comm(self, unique_id, rank, nranks):
         self._ck(lib().mpm_attach_comm(self._h, ctypes.c_char_p(unique_id), rank, nranks))
 
@@ -266,6 +289,15 @@ def polar_batch(A, mode=SVD_EXACT):
     if lib().mpm_polar_batch(_ptr(A), _ptr(R), A.shape[0], mode):
         raise MpmError("mpm_polar_batch failed (no GPU?)")
     return R.reshape(-1, 3, 3)
+
+
+def dinv_batch(x, N):
+    """D^-1 through the generic D_inv of the interpolation kernel at positions x (n x 3): n x 3 x 3."""
+    x = np.ascontiguousarray(x, np.float32).reshape(-1, 3)
+    out = np.empty((x.shape[0], 9), np.float32)
+    if lib().mpm_dinv_batch(_ptr(x), _ptr(out), x.shape[0], N):
+        raise MpmError("mpm_dinv_batch failed (no GPU?)")
+    return out.reshape(-1, 3, 3)
 
 
 def determinant_batch(A):

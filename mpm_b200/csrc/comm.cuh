@@ -39,15 +39,17 @@ __global__ void __launch_bounds__(256) halo_add_kernel(float4* __restrict__ grid
 }
 
 // dest 0 = lower neighbour, 1 = upper neighbour.  Packed layout: stream s of destination d at
-// buf + (d * (NSTREAM + 2) + s) * cap; streams NSTREAM / NSTREAM+1 carry id and material as bits.
+// buf + (d * kMigRows + s) * cap; rows NSTREAM / NSTREAM+1 carry id and material as bits.
+constexpr int kMigRows = NSTREAM + 2;
 __global__ void __launch_bounds__(256) migrate_pack_kernel(Soa p, size_t count, KParams k, float* __restrict__ buf, size_t cap,
                                                            unsigned int* __restrict__ counters) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
   if (p.id[i] == kDeadId) return;
+  const float* __restrict__ c = p.col(i);
   int b;
   float fx, w[3];
-  bspline(p.s(SX)[i], k.dx_inv, b, fx, w);
+  bspline(c[SX * kTile], k.dx_inv, b, fx, w);
   b = min(max(b, 0), k.N - 1);
   int d;
   if (b < k.x_own_begin) d = 0;
@@ -55,21 +57,24 @@ __global__ void __launch_bounds__(256) migrate_pack_kernel(Soa p, size_t count, 
   else return;
   const unsigned int slot = atomicAdd(&counters[d], 1u);
   if (slot < cap) {
-    float* base = buf + (size_t)d * (NSTREAM + 2) * cap + slot;
+    float* base = buf + (size_t)d * kMigRows * cap + slot;
 #pragma unroll
-    for (int s = 0; s < NSTREAM; ++s) base[(size_t)s * cap] = p.s(s)[i];
+    for (int s = 0; s < NSTREAM; ++s) base[(size_t)s * cap] = c[s * kTile];
     base[(size_t)NSTREAM * cap] = __uint_as_float(p.id[i]);
     base[(size_t)(NSTREAM + 1) * cap] = __uint_as_float((uint32_t)p.mat[i]);
   }
   p.id[i] = kDeadId;  // tombstone: sorted behind the live particles by the re-bin that follows
 }
 
-__global__ void __launch_bounds__(256) migrate_unpack_kernel(Soa p, size_t first, size_t n, const float* __restrict__ idbits,
-                                                             const float* __restrict__ matbits) {
+// arrivals from one neighbour (stream-major in `buf`, row stride cap) into slots [first, first + n)
+__global__ void __launch_bounds__(256) migrate_unpack_kernel(Soa p, size_t first, size_t n, const float* __restrict__ buf, size_t cap) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  p.id[first + i] = __float_as_uint(idbits[i]);
-  p.mat[first + i] = (uint8_t)__float_as_uint(matbits[i]);
+  float* __restrict__ c = p.col(first + i);
+#pragma unroll
+  for (int s = 0; s < NSTREAM; ++s) c[s * kTile] = buf[(size_t)s * cap + i];
+  p.id[first + i] = __float_as_uint(buf[(size_t)NSTREAM * cap + i]);
+  p.mat[first + i] = (uint8_t)__float_as_uint(buf[(size_t)(NSTREAM + 1) * cap + i]);
 }
 
 struct Comm {
@@ -83,8 +88,8 @@ struct Comm {
   float4* recv_hi = nullptr;
   // migration
   size_t mig_cap = 0;
-  float* send_buf = nullptr;  // 2 * (NSTREAM+2) * mig_cap
-  float* recv_buf = nullptr;  // 2 * 2 * mig_cap (id + material bits per direction)
+  float* send_buf = nullptr;  // 2 * kMigRows * mig_cap
+  float* recv_buf = nullptr;  // 2 * kMigRows * mig_cap
   unsigned int* d_counts = nullptr;  // [0..1] out, [2..3] in
   unsigned int* h_counts = nullptr;  // pinned mirror
   std::string err;
@@ -104,6 +109,14 @@ struct Comm {
   int failc(const char* what, cudaError_t e) {
     err = std::string(what) + ": " + cudaGetErrorString(e);
     return 1;
+  }
+  // a peer that died or a transport error shows up here, not in the enqueue calls
+  int check_async() {
+    ncclResult_t st = ncclSuccess;
+    const ncclResult_t r = ncclCommGetAsyncError(comm, &st);
+    if (r != ncclSuccess) return fail("ncclCommGetAsyncError", r);
+    if (st != ncclSuccess && st != ncclInProgress) return fail("NCCL asynchronous error", st);
+    return 0;
   }
 
   int init(const void* id128, int rank_, int nranks_, const KParams& k, int ghost, size_t capacity, cudaStream_t) {
@@ -139,9 +152,9 @@ struct Comm {
       if (e != cudaSuccess) return failc("cudaMalloc(recv_hi)", e);
     }
     mig_cap = capacity / 16 + 4096;  // a re-bin may move at most this many particles to one neighbour
-    cudaError_t e = cudaMalloc(&send_buf, sizeof(float) * 2 * (NSTREAM + 2) * mig_cap);
+    cudaError_t e = cudaMalloc(&send_buf, sizeof(float) * 2 * kMigRows * mig_cap);
     if (e != cudaSuccess) return failc("cudaMalloc(send_buf)", e);
-    e = cudaMalloc(&recv_buf, sizeof(float) * 4 * mig_cap);
+    e = cudaMalloc(&recv_buf, sizeof(float) * 2 * kMigRows * mig_cap);
     if (e != cudaSuccess) return failc("cudaMalloc(recv_buf)", e);
     e = cudaMalloc(&d_counts, sizeof(unsigned int) * 4);
     if (e != cudaSuccess) return failc("cudaMalloc(counts)", e);
@@ -222,30 +235,26 @@ struct Comm {
     const size_t first_lo = *count, first_hi = *count + in_lo;
     r = ncclGroupStart();
     if (r != ncclSuccess) return fail("ncclGroupStart", r);
-    for (int s = 0; s < NSTREAM + 2; ++s) {
+    // the packed rows of one direction are one contiguous block only up to the row stride: send row by row
+    for (int s = 0; s < kMigRows; ++s) {
       if (has_lo) {
         if (out_lo) ncclSend(send_buf + (size_t)s * mig_cap, out_lo, ncclFloat, rank - 1, comm, stream);
-        if (in_lo) {
-          float* dst = (s < NSTREAM) ? p.s(s) + first_lo : recv_buf + (size_t)(s - NSTREAM) * mig_cap;
-          ncclRecv(dst, in_lo, ncclFloat, rank - 1, comm, stream);
-        }
+        if (in_lo) ncclRecv(recv_buf + (size_t)s * mig_cap, in_lo, ncclFloat, rank - 1, comm, stream);
       }
       if (has_hi) {
-        if (out_hi) ncclSend(send_buf + (size_t)((NSTREAM + 2) + s) * mig_cap, out_hi, ncclFloat, rank + 1, comm, stream);
-        if (in_hi) {
-          float* dst = (s < NSTREAM) ? p.s(s) + first_hi : recv_buf + (size_t)(2 + s - NSTREAM) * mig_cap;
-          ncclRecv(dst, in_hi, ncclFloat, rank + 1, comm, stream);
-        }
+        if (out_hi) ncclSend(send_buf + (size_t)(kMigRows + s) * mig_cap, out_hi, ncclFloat, rank + 1, comm, stream);
+        if (in_hi) ncclRecv(recv_buf + (size_t)(kMigRows + s) * mig_cap, in_hi, ncclFloat, rank + 1, comm, stream);
       }
     }
     r = ncclGroupEnd();
     if (r != ncclSuccess) return fail("ncclGroupEnd(payload)", r);
+    if (int rc = check_async()) return rc;
     if (in_lo) {
-      migrate_unpack_kernel<<<(unsigned)((in_lo + 255) / 256), 256, 0, stream>>>(p, first_lo, in_lo, recv_buf, recv_buf + mig_cap);
+      migrate_unpack_kernel<<<(unsigned)((in_lo + 255) / 256), 256, 0, stream>>>(p, first_lo, in_lo, recv_buf, mig_cap);
       ++*launches;
     }
     if (in_hi) {
-      migrate_unpack_kernel<<<(unsigned)((in_hi + 255) / 256), 256, 0, stream>>>(p, first_hi, in_hi, recv_buf + 2 * mig_cap, recv_buf + 3 * mig_cap);
+      migrate_unpack_kernel<<<(unsigned)((in_hi + 255) / 256), 256, 0, stream>>>(p, first_hi, in_hi, recv_buf + (size_t)kMigRows * mig_cap, mig_cap);
       ++*launches;
     }
     e = cudaGetLastError();

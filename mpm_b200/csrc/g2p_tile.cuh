@@ -1,102 +1,111 @@
-// Stage (4), production kernel: G2P as a persistent, TMA-fed pipeline
-// (reference behaviour: src/mpm.cu:109-178, TransferScheme.h:102-142).
+// Stage (4), production kernel: G2P as a persistent, bulk-copy-fed pipeline
+// (reference behaviour: src/mpm.cu:109-178, TransferScheme.h:102-142), for the shipped transfer
+// tuple MLS_APIC_Scheme<QuadraticInterpolationKernel> and any MaterialModel.
 //
 // Why: one thread per particle gathering 27 float4 nodes straight from L2 is latency-bound — 64
 // registers hold ~8 of the 27 loads, so every particle pays 3-4 serial L2 round trips on top of
 // the two DRAM round trips for x and F (profiles/r01_ncu_v3_g2p_direct.txt: issue active 48 %,
 // long-scoreboard stalls dominate).  Here the memory system works ahead of the arithmetic:
 //
-//   * Work unit = a tile (tiles.cuh): <= 252 cell-sorted particles of one grid row.  The grid nodes
-//     they can touch form one box (x-1..x+3) x (y-1..y+3) x (z_first-1 .. +LT): ONE 4-D tiled TMA
-//     load (cp.async.bulk.tensor) of 5 x 5 x LT float4.  The particle streams G2P reads (x, F and,
-//     for snow, Jp) are rows 0..12 of the [25][stride] stream tensor: ONE 2-D TMA load.  Nodes
-//     outside the local grid arrive as zeros, which is exactly the reference's stencil clipping
-//     for a gather (src/mpm.cu:137-142), so domain faces and slab edges need no special case.
+//   * Work unit = one 256-particle tile of the SoA (common.cuh).  What G2P reads of it — the stream
+//     rows x, F (and Jp) — is ONE contiguous span of the tile-major layout: a single 1-D bulk copy
+//     (cp.async.bulk, the TMA path without a tensor map) into a shared-memory stage.
 //   * CTA = 8 warps (one thread per particle of the tile) over a ring of kG2pStages stage buffers
 //     with one "full" mbarrier each.  Thread 0 requests the first kG2pStages tiles; afterwards the
 //     warp that releases a stage LAST (a shared-memory counter per stage tells it so) requests the
-//     tile that goes there next, so the two TMA loads of tile it+S run while tile it is computed and
-//     no warp ever waits for another one, only for data.  (A dedicated producer warp did the same
-//     job at first — MPM_G2P_SELFFEED=0 — but made the CTA 288 threads: 3 CTAs per SM instead of 4.)
-//   * A particle finds its stencil at box[(di+i)*5 + (dj+j)][t+k] where (di, dj, t) is its current
-//     base node relative to the box origin.  The box has one cell of slack on every side, so a
-//     particle that drifted at most one cell in any direction since the re-bin is still inside;
-//     the rest take the generic global-memory gather, which clips like the reference.
-//   * The gather is the separable FFMA2 form (kernels.cuh).
-//   * Node source (MPM_G2P_GATHER): 1 (default) = every thread gathers its 27 nodes from global
-//     memory through L1 — the fastest form measured, because a cell-sorted warp's LDG.128 touches one
-//     or two 128-byte lines (1-2 L1 wavefronts) while an LDS.128 always costs four; 0 = the TMA node
-//     box described above; 2 = a per-warp brick in shared memory (DESIGN.md 3.1 has the numbers).
+//     tile that goes there next, so the copy of tile it+S runs while tile it is computed and
+//     no warp ever waits for another one, only for data.  After the first ring fill, tiles are handed
+//     out by a global counter: the B200's two dies do not see the same memory latency and a static
+//     share per CTA ends when the slowest SM is done.
+//   * Every thread gathers its 27 nodes from global memory through L1 — the fastest form measured,
+//     because a cell-sorted warp's LDG.128 touches one or two 128-byte lines (1-2 L1 wavefronts)
+//     while an LDS.128 of a staged node box always costs four (profiles/r01_ab2_session6.txt).
+//     Warps whose particles all have their stencil inside the local grid take a path with no
+//     per-node predicates, in separable FFMA2 form; the others clip per node like the reference.
+//   * EMIT (hand-over, common.cuh): after the F update and the plasticity, the affine matrix of the
+//     NEXT substep's P2G is computed here — F, C, Jp and the material are in registers — and stored
+//     in the C rows, so that P2G reads 15 instead of 25 streams and does not evaluate the material.
 #pragma once
 #include <cuda.h>
 
 #include "kernels.cuh"
-#include "tiles.cuh"
+#include "p2g_sched.cuh"
 #include "tma.cuh"
 
 namespace mpm {
 
-#ifndef MPM_G2P_BOXW
-#define MPM_G2P_BOXW 5  // node box of a tile: BOXW x BOXW rows (5 = one row of slack either side, 3 = exactly the stencil rows)
-#endif
-constexpr int kBoxW = MPM_G2P_BOXW;
-constexpr int kBoxSlack = (kBoxW - 3) / 2;
-constexpr int kBoxRows = kBoxW * kBoxW;
 #ifndef MPM_G2P_STAGES
 #define MPM_G2P_STAGES 3
 #endif
-#ifndef MPM_G2P_TILE_MINBLK
-#define MPM_G2P_TILE_MINBLK 3
-#endif
-#ifndef MPM_G2P_GATHER
-#define MPM_G2P_GATHER 1  // node source: 0 = 5x5xLT TMA box per tile, 1 = global memory per thread, 2 = per-warp brick
-#endif
-#define MPM_G2P_BOX (MPM_G2P_GATHER == 0)
-// With the per-thread global gather nothing ties a tile to one grid row, so tiles are simply the
-// 256-particle blocks of the sorted order: full lanes (row tiles average 228 of 256 particles on the
-// benchmark block) and no tile descriptors.  The shared-memory node sources need row tiles.
-#ifndef MPM_G2P_DYNAMIC
-#define MPM_G2P_DYNAMIC 1  // 1: after the first ring fill, tiles are handed out by a global counter (needs SELFFEED)
-#endif
-#ifndef MPM_G2P_FLAT_TILES
-#define MPM_G2P_FLAT_TILES (MPM_G2P_GATHER == 1)
-#endif
-constexpr int kWarpBrickX = 4, kWarpBrickY = 4, kWarpBrickZ = 16;  // nodes; 4 KB of shared memory per warp
 constexpr int kG2pStages = MPM_G2P_STAGES;
-#ifndef MPM_G2P_SELFFEED
-#define MPM_G2P_SELFFEED 1  // 1: no producer warp — the last warp to release a stage refills it (256 threads, 64 registers, 4 CTAs/SM)
-#endif
-constexpr int kG2pThreads = MPM_G2P_SELFFEED ? kTile : kTile + 32;  // consumers (+ one producer warp)
+constexpr int kG2pThreads = kTile;
+constexpr int kG2pRows = NSTREAM - SX;  // stream rows x, F, Jp = 13, contiguous in a tile
+static_assert(SX == 12 && SF == 15 && SJ == 24, "G2P reads stream rows 12..24 as one span");
 
-struct TileHeader {  // written by the producer next to each stage
-  int x0b, y0b, z0b;   // box origin in local grid coordinates (may be -1)
-  int n;               // particles in the tile
-  unsigned int start;  // first particle slot
-  int off;             // start & 3: column of the first particle in the stream box
-  int pad_[2];
-};
+#define MPM_STP(ptr, val) __stcs(ptr, val)  // particle streams are touched once per kernel: streaming stores
 
-template <int MODEL>
 struct G2pTileLayout {
-  static constexpr int kStreams = (MODEL == MPM_MODEL_SNOW) ? 13 : 12;  // x3, F9 (, Jp) = stream rows 0..kStreams-1
-  __host__ __device__ static constexpr size_t box_bytes(int LT) { return MPM_G2P_BOX ? (size_t)kBoxRows * LT * 16 : 0; }
-  __host__ __device__ static constexpr size_t stream_bytes() { return (size_t)kStreams * kTile * 4; }
-  __host__ __device__ static constexpr size_t stage_bytes(int LT) { return box_bytes(LT) + stream_bytes(); }
-  __host__ __device__ static constexpr size_t brick_bytes() {
-    return MPM_G2P_GATHER == 2 ? (size_t)(kTile / 32) * kWarpBrickX * kWarpBrickY * kWarpBrickZ * 16 : 0;
-  }
-  // stages + per-warp bricks + headers + barriers + slack for 128-byte alignment of the first stage
-  __host__ __device__ static constexpr size_t bytes(int LT) {
-    return kG2pStages * (stage_bytes(LT) + sizeof(TileHeader) + 16) + brick_bytes() + 128;
-  }
+  // Jp is the last row: materials that never read it get a 12-row copy
+  __host__ __device__ static constexpr size_t stage_bytes(bool with_jp) { return (size_t)(with_jp ? kG2pRows : kG2pRows - 1) * kTile * 4; }
+  // stages + tile indices + barriers + release counters + slack for 128-byte alignment of the first stage
+  __host__ __device__ static constexpr size_t bytes(bool with_jp) { return kG2pStages * (stage_bytes(with_jp) + 32) + 128; }
 };
 
-// separable FFMA2 gather of the 27 stencil nodes starting at tp (row_stride / plane_stride in nodes)
+// generic gather with per-node clipping (domain faces, slab edges); B = sum_i w v_i d_i^T.
+// Deliberately not inlined and fed by value: the rare clipped warps pay a call, the interior path
+// keeps its registers.
+struct G2pGather {
+  float v[3];
+  float B[3][3];
+};
+static __device__ __noinline__ G2pGather g2p_gather_clipped(const float4* __restrict__ grid, KParams k, float x0, float x1, float x2) {
+  const float x[3] = {x0, x1, x2};
+  int base[3];
+  float fx[3], w[3][3], d[3][3];
+  for (int a = 0; a < 3; ++a) {
+    bspline(x[a], k.dx_inv, base[a], fx[a], w[a]);
+    for (int i = 0; i < 3; ++i) d[a][i] = (float)(base[a] + i) * k.dx - x[a];
+  }
+  G2pGather o;
+  for (int c = 0; c < 3; ++c) {
+    o.v[c] = 0.f;
+    for (int a = 0; a < 3; ++a) o.B[c][a] = 0.f;
+  }
+  const long long NN = (long long)k.N * k.N;
+  const float4* gbase = grid + ((long long)(base[0] - k.x0) * NN + (long long)base[1] * k.N + base[2]);
+  for (int i = 0; i < 3; ++i) {
+    const int gx = base[0] + i;
+    if (gx < 0 || gx >= k.N || gx < k.x0 || gx >= k.x0 + k.nxl) continue;
+    for (int j = 0; j < 3; ++j) {
+      const int gy = base[1] + j;
+      if (gy < 0 || gy >= k.N) continue;
+      const float wij = w[0][i] * w[1][j];
+      for (int kz = 0; kz < 3; ++kz) {
+        const int gz = base[2] + kz;
+        if (gz < 0 || gz >= k.N) continue;
+        const float4 g = __ldg(gbase + ((long long)i * NN + j * k.N + kz));
+        const float wt = wij * w[2][kz];
+        const float wv[3] = {wt * g.x, wt * g.y, wt * g.z};
+        for (int c = 0; c < 3; ++c) {
+          o.v[c] += wv[c];
+          o.B[c][0] += wv[c] * d[0][i];
+          o.B[c][1] += wv[c] * d[1][j];
+          o.B[c][2] += wv[c] * d[2][kz];
+        }
+      }
+    }
+  }
+  return o;
+}
+
+// separable FFMA2 gather of the 27 stencil nodes starting at tp (row_stride / plane_stride in nodes):
+// per (i, j) row s0 = sum_k wz_k v_k and s1 = sum_k wz_k dz_k v_k (the three k-nodes are one
+// contiguous 48 B run), then one rank-1 update of (v, B) per row; x, y components travel as packed
+// pairs (f32x2.cuh), z as scalars
 struct G2pAcc {
   float v[3];
-  Mat3 B;  // sum_i w v_i d_i^T
+  Mat B;  // sum_i w v_i d_i^T
 };
-template <bool GLOBAL>
 __device__ __forceinline__ void g2p_gather27(const float4* __restrict__ tp, long long row_stride, long long plane_stride,
                                              const float w[3][3], const float d[3][3], G2pAcc& o) {
   float wzd[3], wxd[3], wyd[3];
@@ -116,12 +125,7 @@ __device__ __forceinline__ void g2p_gather27(const float4* __restrict__ tp, long
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       const float4* row = tp + (i * plane_stride + j * row_stride);
-      float4 g0, g1, g2;
-      if (GLOBAL) {
-        g0 = __ldg(row); g1 = __ldg(row + 1); g2 = __ldg(row + 2);
-      } else {
-        g0 = row[0]; g1 = row[1]; g2 = row[2];
-      }
+      const float4 g0 = __ldg(row), g1 = __ldg(row + 1), g2 = __ldg(row + 2);
       f2 s0 = mul2(WZ[0], pack2(g0.x, g0.y));
       f2 s1 = mul2(WZD[0], pack2(g0.x, g0.y));
       float s0z = w[2][0] * g0.z, s1z = wzd[0] * g0.z;
@@ -151,16 +155,12 @@ __device__ __forceinline__ void g2p_gather27(const float4* __restrict__ tp, long
   o.B.m[0][2] = lo2(B2xy); o.B.m[1][2] = hi2(B2xy); o.B.m[2][2] = B2z;
 }
 
-template <int MODEL, class O, int LT, bool COUNT_MOVED>
-__device__ __forceinline__ void g2p_tile_compute(const Soa& p, const MpmMaterial* __restrict__ mats, const MpmMaterial& mat0, bool one_mat,
-                                                 const float4* __restrict__ grid,
-                                                 const KParams& k, const TileHeader& h, const float4* __restrict__ box,
-                                                 float4* __restrict__ wtile, const float* __restrict__ ps, int tid, unsigned& moved) {
-  const bool live = tid < h.n;
-  const size_t pi = (size_t)h.start + tid;
-  uint8_t mat_id = 0;
-  if (MODEL == MPM_MODEL_SNOW && live && !one_mat) mat_id = p.mat[pi];
-  ps += h.off + tid;  // this particle's column of the stream box
+// one particle of a staged tile: ps = this particle's column of the stage (rows x, F, Jp), col = its
+// column of the tile in HBM
+template <class Material, bool ONE_MAT, bool EMIT>
+__device__ __forceinline__ void g2p_tile_compute(const Soa& p, const MatTable<Material>& mats, const float4* __restrict__ grid, const KParams& k,
+                                                 const float* __restrict__ ps, float* __restrict__ col, size_t pi, bool live, bool with_jp,
+                                                 bool count_moved, unsigned& moved) {
   float x[3];
 #pragma unroll
   for (int a = 0; a < 3; ++a) x[a] = live ? ps[a * kTile] : 0.f;
@@ -168,255 +168,148 @@ __device__ __forceinline__ void g2p_tile_compute(const Soa& p, const MpmMaterial
   float fx[3], w[3][3];
 #pragma unroll
   for (int a = 0; a < 3; ++a) bspline(x[a], k.dx_inv, base[a], fx[a], w[a]);
-  bool valid = live;
+  const bool valid = live && !stencil_outside(base, k.N);  // else untouched (reference early return)
+  const int bxl = base[0] - k.x0;                           // x-plane in the local grid
+  bool interior = bxl >= 0 && bxl + 2 < k.nxl;
 #pragma unroll
-  for (int a = 0; a < 3; ++a) valid = valid && !(base[a] + 3 < 0 || base[a] >= k.N);  // else untouched (reference early return)
-  const int bxl = base[0] - k.x0;  // x-plane in the local grid
-  float d[3][3];  // node - particle distance per axis (world units)
-#pragma unroll
-  for (int a = 0; a < 3; ++a)
-#pragma unroll
-    for (int i = 0; i < 3; ++i) d[a][i] = (float)(base[a] + i) * k.dx - x[a];
+  for (int a = 0; a < 3; ++a) interior = interior && base[a] >= 0 && base[a] + 2 < k.N;
+  if (!valid) return;
 
   G2pAcc acc;
-  bool gathered = false;
-#if MPM_G2P_GATHER == 0
-  // ---- nodes from the tile's TMA box: stencil = box rows (di..di+2, dj..dj+2), nodes t..t+2 ----
-  {
-    const int di = bxl - h.x0b, dj = base[1] - h.y0b, t = base[2] - h.z0b;
-    if (valid && (unsigned)di <= (unsigned)(kBoxW - 3) && (unsigned)dj <= (unsigned)(kBoxW - 3) && (unsigned)t <= (unsigned)(LT - 3)) {
-      g2p_gather27<false>(box + (di * kBoxW + dj) * LT + t, LT, kBoxW * LT, w, d, acc);
-      gathered = true;
+  if (interior) {  // whole stencil inside the local grid: unclipped gather
+    float d[3][3];  // node - particle distance per axis (world units)
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int i = 0; i < 3; ++i) d[a][i] = (float)(base[a] + i) * k.dx - x[a];
+    const long long NN = (long long)k.N * k.N;
+    g2p_gather27(grid + (bxl * NN + (long long)base[1] * k.N + base[2]), k.N, NN, w, d, acc);
+  } else {
+    const G2pGather o = g2p_gather_clipped(grid, k, x[0], x[1], x[2]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      acc.v[c] = o.v[c];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) acc.B.m[c][a] = o.B[c][a];
     }
   }
-#elif MPM_G2P_GATHER == 2
-  // ---- nodes staged per warp: the 32 particles of a warp are neighbours in the sorted order, so
-  // their stencils cover a small brick.  Bounding box by redux, every lane fetches its share of
-  // the brick (one batch of independent loads = ONE L2 round trip per warp instead of the 6-7
-  // register-limited batches of a per-thread gather), then the stencil is read from shared memory.
-  {
-    constexpr int XT = kWarpBrickX, YT = kWarpBrickY, ZT = kWarpBrickZ;
-    const int big = 0x3fffffff;
-    const int mnx = __reduce_min_sync(0xffffffffu, valid ? bxl : big), mxx = __reduce_max_sync(0xffffffffu, valid ? bxl : -big);
-    const int mny = __reduce_min_sync(0xffffffffu, valid ? base[1] : big), mxy = __reduce_max_sync(0xffffffffu, valid ? base[1] : -big);
-    const int mnz = __reduce_min_sync(0xffffffffu, valid ? base[2] : big), mxz = __reduce_max_sync(0xffffffffu, valid ? base[2] : -big);
-    const int ex = mxx - mnx + 3, ey = mxy - mny + 3, ez = mxz - mnz + 3;  // brick extent in nodes
-    if (mxx >= mnx && ex <= XT && ey <= YT && ez <= ZT) {
-      const int lane = tid & 31;
-      const long long NN = (long long)k.N * k.N;
-      constexpr int kIt = XT * YT * ZT / 32;
-      float4 g[kIt];
-      // all loads first (independent, predicated, no branches), then all stores: one round trip
-#pragma unroll
-      for (int it = 0; it < kIt; ++it) {
-        const int slot = it * 32 + lane;
-        const int iz = slot % ZT, iy = (slot / ZT) % YT, ix = slot / (ZT * YT);
-        const int gx = mnx + ix, gy = mny + iy, gz = mnz + iz;
-        const bool need = ix < ex && iy < ey && iz < ez;
-        // outside the local grid: zero = the reference's clipping
-        const bool inb = need && (unsigned)gx < (unsigned)k.nxl && (unsigned)gy < (unsigned)k.N && (unsigned)gz < (unsigned)k.N;
-        const float4* src = grid + (inb ? (gx * NN + (long long)gy * k.N + gz) : 0ll);
-        g[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (inb) g[it] = __ldg(src);
-      }
-#pragma unroll
-      for (int it = 0; it < kIt; ++it) {
-        const int slot = it * 32 + lane;
-        const int iz = slot % ZT, iy = (slot / ZT) % YT, ix = slot / (ZT * YT);
-        if (ix < ex && iy < ey && iz < ez) wtile[slot] = g[it];
-      }
-      __syncwarp();
-      if (valid) {
-        g2p_gather27<false>(wtile + ((bxl - mnx) * YT + (base[1] - mny)) * ZT + (base[2] - mnz), ZT, YT * ZT, w, d, acc);
-        gathered = true;
-      }
-    }
-  }
-#endif
-  if (!valid) return;
-#if defined(MPM_G2P_EXP) && (MPM_G2P_EXP & 1)  // experiment: no gather at all
-  gathered = true;
-  for (int c = 0; c < 3; ++c) { acc.v[c] = x[c]; for (int a = 0; a < 3; ++a) acc.B.m[c][a] = w[c][a]; }
-#endif
-  if (!gathered) {
-    bool interior = bxl >= 0 && bxl + 2 < k.nxl;
-#pragma unroll
-    for (int a = 0; a < 3; ++a) interior = interior && base[a] >= 0 && base[a] + 2 < k.N;
-    if (interior) {  // whole stencil inside the local grid: unclipped gather from global memory
-      const long long NN = (long long)k.N * k.N;
-      g2p_gather27<true>(grid + (bxl * NN + (long long)base[1] * k.N + base[2]), k.N, NN, w, d, acc);
-    } else {
-      const G2pGather o = g2p_gather_clipped(grid, k, x[0], x[1], x[2]);
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        acc.v[c] = o.v[c];
-#pragma unroll
-        for (int a = 0; a < 3; ++a) acc.B.m[c][a] = o.B[c][a];
-      }
-    }
-  }
-  const float* v = acc.v;
-  const Mat3& B = acc.B;
-  Mat3 C, G, F;
+  Particle part;
+  part.material_type = 0;
+  Mat G;
 #pragma unroll
   for (int r = 0; r < 3; ++r)
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      C.m[r][c] = B.m[r][c] * k.dinv;
-      G.m[r][c] = ((r == c) ? 1.0f : 0.0f) + k.dt * C.m[r][c];
-      F.m[r][c] = ps[(SF + 3 * r + c) * kTile];
+      part.C.m[r][c] = acc.B.m[r][c] * k.dinv;
+      G.m[r][c] = ((r == c) ? 1.0f : 0.0f) + k.dt * part.C.m[r][c];
+      part.F.m[r][c] = ps[(SF - SX + 3 * r + c) * kTile];
     }
-  F = mul_ab(G, F);  // F <- (I + dt C) F
-  if (MODEL == MPM_MODEL_SNOW) {
-    float Jp = ps[SJ * kTile];
-    // single-material handles read the clamps straight from the kernel parameters (uniform branch)
-    const MpmMaterial m = one_mat ? mat0 : load_material(mats, mat_id);
-    snow_plasticity<O>(F, Jp, m);
-    MPM_STP(p.s(SJ) + pi, Jp);
-  }
+  part.F = G * part.F;  // F <- (I + dt C) F  (g2p_finish_particle)
+  constexpr bool kJp = MaterialTraits<Material>::kMutatesJp;
+  part.Jp = 1.0f;
+  if (kJp) part.Jp = ps[(SJ - SX) * kTile];
+  else if (EMIT && with_jp) part.Jp = col[SJ * kTile];  // read-only Jp != 1 of a fixed-corotated handle
+  const Material m = mats.template get<ONE_MAT>(p.mat, pi);
+  m.endOfStepMutation(part);
+  if (kJp) MPM_STP(col + SJ * kTile, part.Jp);
   bool crossed = false;  // did the advection take the particle into another cell (rebin_permille, mpm_b200.h)
+  int nbase[3];
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
-    const float xn = x[a] + k.dt * v[a];
-    if (COUNT_MOVED) crossed = crossed || ((int)(xn * k.dx_inv - 0.5f) != base[a]);
-    MPM_STP(p.s(SX + a) + pi, xn);
-    MPM_STP(p.s(SV + a) + pi, v[a]);
+    const float xn = x[a] + k.dt * acc.v[a];
+    part.x(a) = xn;
+    part.v(a) = acc.v[a];
+    nbase[a] = (int)(xn * k.dx_inv - 0.5f);
+    crossed = crossed || (nbase[a] != base[a]);
+    MPM_STP(col + (SX + a) * kTile, xn);
+    MPM_STP(col + (SV + a) * kTile, acc.v[a]);
   }
-  if (COUNT_MOVED) moved += crossed ? 1u : 0u;
-#if defined(MPM_G2P_EXP) && (MPM_G2P_EXP & 2)  // experiment: 6 of the 24 output streams only
-  if (F.m[0][0] + C.m[1][1] + F.m[2][2] + C.m[0][2] == 12345.f) MPM_STP(p.s(SF) + pi, 0.f);
-#else
+  if (count_moved) moved += crossed ? 1u : 0u;
+  Mat out = part.C;
+  if (EMIT) {
+    // the next P2G skips a particle whose stencil has left the domain, and so does every G2P after
+    // it: such a particle keeps C (the state the reference would hold), everyone else gets dx * affine
+    if (!stencil_outside(nbase, k.N)) out = p2g_affine_dx(part, m, k);
+  }
 #pragma unroll
   for (int r = 0; r < 3; ++r)
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      MPM_STP(p.s(SF + 3 * r + c) + pi, F.m[r][c]);
-      MPM_STP(p.s(SC + 3 * r + c) + pi, C.m[r][c]);
+      MPM_STP(col + (SF + 3 * r + c) * kTile, part.F.m[r][c]);
+      MPM_STP(col + (SC + 3 * r + c) * kTile, out.m[r][c]);
     }
-#endif
 }
 
-// Persistent CTAs: tile `it` of this CTA = blockIdx.x + it * gridDim.x.
-template <int MODEL, class O, int LT, bool COUNT_MOVED>
-__global__ void __launch_bounds__(kG2pThreads, MPM_G2P_SELFFEED ? 4 : MPM_G2P_TILE_MINBLK)
-g2p_tile_kernel(Soa p, const MpmMaterial* __restrict__ mats, const MpmMaterial mat0, const bool one_mat, const float4* __restrict__ grid, KParams k,
-                const TileDesc* __restrict__ tiles, const uint32_t* __restrict__ n_tiles_ptr,
-                const __grid_constant__ CUtensorMap tm_grid, const __grid_constant__ CUtensorMap tm_streams,
-                unsigned long long* __restrict__ moved_total, size_t count, unsigned int* __restrict__ tile_counters, int parity) {
-  using L = G2pTileLayout<MODEL>;
-  static_assert(SX == 0 && SF == 3 && SJ == 12, "G2P reads stream rows 0..12 as one TMA box");
+// Persistent CTAs: the first kG2pStages tiles of CTA b are b, b + gridDim.x, ...; afterwards tiles come
+// from tile_counters[parity] (the other counter is reset for the next launch).
+template <class Material, bool ONE_MAT, bool EMIT>
+__global__ void __launch_bounds__(kG2pThreads, 4)
+g2p_tile_kernel(Soa p, const MatTable<Material> mats, const float4* __restrict__ grid, KParams k, size_t count,
+                unsigned long long* __restrict__ moved_total, unsigned int* __restrict__ tile_counters, int parity,
+                const DeviceDiag* __restrict__ diag) {
   extern __shared__ unsigned char smem_dyn[];
-  unsigned char* smem = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);  // TMA destinations: 128 B aligned
-  constexpr size_t kStage = L::stage_bytes(LT);
-  float4* bricks = reinterpret_cast<float4*>(smem + kG2pStages * kStage);
-  TileHeader* hdr = reinterpret_cast<TileHeader*>(smem + kG2pStages * kStage + L::brick_bytes());
-  uint64_t* full = reinterpret_cast<uint64_t*>(hdr + kG2pStages);
-  uint64_t* empty = full + kG2pStages;
+  unsigned char* smem = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);  // bulk-copy destinations: 128 B aligned
+  constexpr bool kJp = MaterialTraits<Material>::kMutatesJp;
+  constexpr size_t kStage = G2pTileLayout::stage_bytes(kJp);
+  uint32_t* tile_of = reinterpret_cast<uint32_t*>(smem + kG2pStages * kStage);  // tile index in each stage, 0xffffffff = end
+  uint64_t* full = reinterpret_cast<uint64_t*>(tile_of + 2 * kG2pStages);
+  uint32_t* rel = reinterpret_cast<uint32_t*>(full + kG2pStages);              // warps done with each stage
   const int tid = threadIdx.x;
-  const uint32_t n_tiles = MPM_G2P_FLAT_TILES ? (uint32_t)((count + kTile - 1) / kTile) : *n_tiles_ptr;
+  const uint32_t n_tiles = (uint32_t)((count + kTile - 1) / kTile);
+  const bool with_jp = kJp || (EMIT && diag->jp_not_one != 0);
+
+  // one bulk copy: rows x, F (, Jp) of tile t into stage s
+  auto issue = [&](uint32_t t, int s) {
+    tile_of[s] = t;
+    mbar_arrive_expect_tx(full + s, (uint32_t)kStage);
+    bulk_g2s(smem + s * kStage, p.tile(t) + SX * kTile, (uint32_t)kStage, full + s);
+  };
   if (tid == 0) {
     for (int s = 0; s < kG2pStages; ++s) {
       mbar_init(full + s, 1);
-      mbar_init(empty + s, kTile / 32);
+      rel[s] = 0;
     }
     mbar_fence_init();
-  }
-  __syncthreads();
-
-  // one TMA request: header + stream rows (+ node box) of tile t into stage s
-  auto issue = [&](uint32_t t, int s) {
-    TileDesc d;
-    if (MPM_G2P_FLAT_TILES) {
-      d.start = t * (uint32_t)kTile;
-      d.n = (uint32_t)min((size_t)kTile, count - (size_t)d.start);
-      d.kfirst = d.klast = 0;
-    } else {
-      d = tiles[t];
-    }
-    const uint32_t row = d.kfirst / (uint32_t)k.N;
-    TileHeader h;
-    h.z0b = (int)(d.kfirst - row * (uint32_t)k.N) - 1;
-    h.x0b = (int)(row / (uint32_t)k.N);
-    h.y0b = (int)(row - (uint32_t)h.x0b * (uint32_t)k.N) - kBoxSlack;
-    h.x0b -= kBoxSlack;
-    h.n = (int)d.n;
-    h.start = d.start;
-    h.off = (int)(d.start & 3u);
-    hdr[s] = h;
-    unsigned char* st = smem + s * kStage;
-    mbar_arrive_expect_tx(full + s, (uint32_t)kStage);
-    if (MPM_G2P_BOX) tma_load_4d(st, &tm_grid, 0, h.z0b, h.y0b, h.x0b, full + s);
-    tma_load_2d(st + L::box_bytes(LT), &tm_streams, (int)(d.start & ~3u), 0, full + s);
-  };
-#if MPM_G2P_SELFFEED
-  // No producer warp: thread 0 fills the ring once, afterwards the LAST warp to finish with a stage
-  // (a shared-memory counter tells it so) requests the tile that goes there next.  Nobody waits.
-  uint32_t* rel = reinterpret_cast<uint32_t*>(empty);  // the "empty" barriers are unused: one counter per stage
-  if (tid == 0) {
-    tma_prefetch_desc(&tm_streams);
     for (int s = 0; s < kG2pStages; ++s) {
-      rel[2 * s] = 0;
       const uint32_t t = blockIdx.x + (uint32_t)s * gridDim.x;
       if (t < n_tiles) {
         issue(t, s);
-      } else if (MPM_G2P_DYNAMIC) {  // end marker
-        hdr[s].n = -1;
+      } else {  // end marker
+        tile_of[s] = 0xffffffffu;
         mbar_arrive(full + s);
       }
     }
-    if (MPM_G2P_DYNAMIC && blockIdx.x == 0) tile_counters[parity ^ 1] = 0;  // the next launch's counter
+    if (blockIdx.x == 0) tile_counters[parity ^ 1] = 0;  // the next launch's counter
   }
   __syncthreads();
-#else
-  if (tid >= kTile) {  // ---- producer warp: one elected lane feeds the ring ----
-    if (tid == kTile) {
-      tma_prefetch_desc(&tm_grid);
-      tma_prefetch_desc(&tm_streams);
-      int it = 0;
-      for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-        const int s = it % kG2pStages;
-        if (it >= kG2pStages) mbar_wait(empty + s, (uint32_t)(((it / kG2pStages) - 1) & 1));
-        issue(t, s);
-      }
-    }
-    return;
-  }
-#endif
-  // ---- consumer warps ----
-  int it = 0;
+
   unsigned moved = 0;  // particles of this thread that changed cell in this substep
-  for (uint32_t t = blockIdx.x; MPM_G2P_DYNAMIC || t < n_tiles; t += gridDim.x, ++it) {
+  for (int it = 0;; ++it) {
     const int s = it % kG2pStages;
     mbar_wait(full + s, (uint32_t)((it / kG2pStages) & 1));
-    if (MPM_G2P_DYNAMIC && hdr[s].n < 0) break;  // no more tiles for this CTA
-    const unsigned char* st = smem + s * kStage;
-    g2p_tile_compute<MODEL, O, LT, COUNT_MOVED>(p, mats, mat0, one_mat, grid, k, hdr[s], reinterpret_cast<const float4*>(st),
-                                   bricks + (tid >> 5) * (kWarpBrickX * kWarpBrickY * kWarpBrickZ),
-                                   reinterpret_cast<const float*>(st + L::box_bytes(LT)), tid, moved);
-    __syncwarp();  // stage s and the warp's brick are free again
-#if MPM_G2P_SELFFEED
+    const uint32_t t = tile_of[s];
+    if (t == 0xffffffffu) break;  // no more tiles for this CTA
+    const size_t pi = (size_t)t * kTile + tid;
+    g2p_tile_compute<Material, ONE_MAT, EMIT>(p, mats, grid, k, reinterpret_cast<const float*>(smem + s * kStage) + tid, p.tile(t) + tid, pi,
+                                              pi < count, with_jp, moved_total != nullptr, moved);
+    __syncwarp();  // the warp is done with stage s
     if ((tid & 31) == 0) {
       __threadfence_block();
-      if (atomicAdd(&rel[2 * s], 1u) == kTile / 32 - 1) {
-        rel[2 * s] = 0;
+      if (atomicAdd(&rel[s], 1u) == kTile / 32 - 1) {  // last warp out refills the stage
+        rel[s] = 0;
         __threadfence_block();
-        // static: the tile kG2pStages rounds ahead; dynamic: the next tile nobody has taken yet
-        const uint32_t tn = MPM_G2P_DYNAMIC ? (uint32_t)kG2pStages * gridDim.x + atomicAdd(&tile_counters[parity], 1u)
-                                            : t + (uint32_t)kG2pStages * gridDim.x;
+        const uint32_t tn = (uint32_t)kG2pStages * gridDim.x + atomicAdd(&tile_counters[parity], 1u);
         if (tn < n_tiles) {
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the warps' reads of the stage before the copy engine's writes
           issue(tn, s);
-        } else if (MPM_G2P_DYNAMIC) {
-          hdr[s].n = -1;
+        } else {
+          tile_of[s] = 0xffffffffu;
           mbar_arrive(full + s);
         }
       }
     }
-#else
-    if ((tid & 31) == 0) mbar_arrive(empty + s);
-#endif
   }
-  if (COUNT_MOVED) {
+  if (moved_total) {
     moved = __reduce_add_sync(0xffffffffu, moved);
     if ((tid & 31) == 0 && moved) atomicAdd(moved_total, (unsigned long long)moved);
   }

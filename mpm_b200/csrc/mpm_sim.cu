@@ -2,6 +2,7 @@
 // Replaces the device side of the reference's Simulation class (src/mpm.cu:180-329).
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <algorithm>
 #include <cmath>
@@ -9,22 +10,53 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 
 #include "../../include/mpm_b200.h"
 #include "comm.cuh"
-#include "kernels.cuh"
-#include "g2p_tile.cuh"
-#include "g2p2g.cuh"
-#include "p2g_sched.cuh"
+#include "handle_kernels.cuh"
 #include "sort.cuh"
+#include "substep.cuh"
 
 using namespace mpm;
 
-constexpr int kLtSmall = 48, kLtLarge = 96;  // box lengths the staged kernels are instantiated for
-
 static thread_local std::string g_create_error;
+
+// ---- model registry (substep.cuh) -----------------------------------------------------------------
+namespace mpm {
+namespace {
+constexpr int kMaxModels = 64;
+const ModelOps* g_models[kMaxModels][2];
+std::mutex g_models_mu;
+}  // namespace
+int register_model(uint32_t id, const ModelOps* exact, const ModelOps* fast) {
+  if (id >= (uint32_t)kMaxModels || !exact || !fast) return 1;
+  std::lock_guard<std::mutex> lock(g_models_mu);
+  g_models[id][0] = exact;
+  g_models[id][1] = fast;
+  return 0;
+}
+const ModelOps* find_model(uint32_t id, uint32_t svd_mode) {
+  if (id >= (uint32_t)kMaxModels || svd_mode > 1) return nullptr;
+  std::lock_guard<std::mutex> lock(g_models_mu);
+  return g_models[id][svd_mode];
+}
+// the shipped models, one translation unit each (models_*.cu)
+const ModelOps* model_snow(int svd_mode);
+const ModelOps* model_fixed_corotated(int svd_mode);
+const ModelOps* model_jelly(int svd_mode);
+namespace {
+struct ShippedModels {
+  ShippedModels() {
+    register_model(MPM_MODEL_SNOW, model_snow(0), model_snow(1));
+    register_model(MPM_MODEL_FIXED_COROTATED, model_fixed_corotated(0), model_fixed_corotated(1));
+    register_model(MPM_MODEL_JELLY, model_jelly(0), model_jelly(1));
+  }
+} g_shipped_models;
+}  // namespace
+}  // namespace mpm
 
 struct MpmSim {
   MpmParams par{};
@@ -32,26 +64,25 @@ struct MpmSim {
   int device = 0;
   int n_sms = 148;
   cudaStream_t stream = nullptr;
+  const ModelOps* ops = nullptr;
 
-  // particles: two SoA buffers (sort permutes from one into the other)
+  // particles: two SoA buffers (the re-bin permutes from one into the other)
   Soa soa[2]{};
   int cur = 0;
   size_t capacity = 0;
   size_t count = 0;
   uint32_t first_id = 0;
+  // what the C rows of the particles hold: the APIC matrix C (always, at the API boundary) or
+  // dx * affine of the next P2G (between two substeps of one mpm_advance call, common.cuh)
+  bool form_ad = false;
+  bool handover = false;  // the pipeline hands over (MPM_PIPE_HANDOVER with the staged kernels)
 
   // grid: nxl * N * N float4
   float4* grid = nullptr;
   size_t grid_nodes = 0;
-  // fused mode (g2p2g.cuh): second grid, the two swap roles every substep.  grid_ready = `grid`
-  // already holds the updated velocities of the NEXT substep (scattered by the previous fused
-  // kernel from the particles' current state); any change to the particles or the grid clears it.
-  float4* grid_b = nullptr;
-  bool fused = false;
-  bool grid_ready = false;
 
-  MpmMaterial* mats = nullptr;
-  MpmMaterial mat0{};  // host copy of material 0: single-material handles pass it as a kernel parameter
+  void* mats_dev = nullptr;   // n_mats objects of the model's material type
+  void* mats_host = nullptr;
   int n_mats = 0;
 
   // sort scratch
@@ -65,29 +96,12 @@ struct MpmSim {
   int ghost = 0;
   bool whole_domain = true;
   int sorted_cur = 0;  // which keys[] buffer holds the keys of the current order
-  // particle tiles of the staged kernels (tiles.cuh), rebuilt at every re-bin
-  TileDesc* tiles = nullptr;
-  size_t tiles_cap = 0;
-  uint32_t* row_first = nullptr;  // n_rows + 1
-  uint32_t* tile_base = nullptr;  // n_rows + 1
-  uint32_t* d_n_tiles = nullptr;
-  uint32_t n_rows = 0;
-  // box length (nodes along z) of the staged kernels, chosen from the measured cell span of the
-  // tiles at the last re-bin (read back asynchronously, never waited for)
-  int tile_lt = kLtLarge;
-  unsigned int* d_span = nullptr;  // [0] tiles whose box fits kLtSmall, [1] tiles
-  unsigned int* h_span = nullptr;  // pinned mirror
-  cudaEvent_t span_ev = nullptr;
-  bool span_pending = false;
-  // TMA descriptors: grid as [nxl][N][N][4 floats] with a 5 x 5 x LT box; particle streams of
-  // each SoA buffer as [NSTREAM][stride] with kTile-column boxes of 12 / 13 / 25 rows
-  CUtensorMap tm_grid[2];         // kLtSmall, kLtLarge
-  CUtensorMap tm_grid_b[2];       // the same over grid_b (fused mode)
-  CUtensorMap tm_streams[2][3];   // [soa buffer][12, 13, 25 rows]
 
   MpmParticle* aos_stage = nullptr;  // device AoS staging for upload/download
   size_t aos_stage_cap = 0;
   unsigned long long* d_counter = nullptr;
+  DeviceDiag* d_diag = nullptr;
+  DeviceDiag* h_diag = nullptr;  // pinned
 
   // adaptive re-bin (MpmParams.rebin_permille): cell crossings counted by the G2P tile kernel since the
   // last re-bin, read back asynchronously (never waited for)
@@ -109,6 +123,16 @@ struct MpmSim {
   bool timing = false;
   cudaEvent_t ev[2]{};
   float stage_ms[MPM_STAGE_COUNT]{};
+
+  // slab handles: the halo exchange runs on its own stream while the interior particles scatter
+  // (see do_p2g_and_exchange).  split[0..1] = tiles whose particles can touch the planes shared with
+  // the lower neighbour / first tile of those that can touch the planes shared with the upper one.
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_boundary = nullptr, ev_exchanged = nullptr;
+  uint32_t* d_split = nullptr;
+  uint32_t* h_split = nullptr;  // pinned
+  cudaEvent_t split_ev = nullptr;
+  bool split_pending = false, split_valid = false;
 
   Comm comm;
   std::string err;
@@ -132,63 +156,11 @@ int fail(MpmSim* s, const char* fmt, ...) {
     if (e_ != cudaSuccess) return fail(sim, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)) ? (int)e_ : (int)e_; \
   } while (0)
 
-inline unsigned blocks_for(size_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn encode_tiled() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(ptr);
-  }
-  return fn;
-}
-
-int make_stream_maps(MpmSim* sim, int buf) {
-  EncodeTiledFn enc = encode_tiled();
-  if (!enc) return fail(sim, "cuTensorMapEncodeTiled is not available from this driver");
-  const Soa& s = sim->soa[buf];
-  const int rows[3] = {12, 13, NSTREAM};
-  for (int r = 0; r < 3; ++r) {
-    const cuuint64_t dims[2] = {(cuuint64_t)s.stride, (cuuint64_t)NSTREAM};
-    const cuuint64_t strides[1] = {(cuuint64_t)s.stride * sizeof(float)};
-    const cuuint32_t box[2] = {(cuuint32_t)kTile, (cuuint32_t)rows[r]};
-    const cuuint32_t estr[2] = {1, 1};
-    const CUresult rc = enc(&sim->tm_streams[buf][r], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, s.f, dims, strides, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (rc != CUDA_SUCCESS) return fail(sim, "cuTensorMapEncodeTiled(streams) failed: %d", (int)rc);
-  }
-  return 0;
-}
-
-int make_grid_maps(MpmSim* sim, float4* grid, CUtensorMap* out) {
-  EncodeTiledFn enc = encode_tiled();
-  if (!enc) return fail(sim, "cuTensorMapEncodeTiled is not available from this driver");
-  const cuuint64_t N = (cuuint64_t)sim->k.N;
-  const int lts[2] = {kLtSmall, kLtLarge};
-  for (int i = 0; i < 2; ++i) {
-    const cuuint64_t dims[4] = {4, N, N, (cuuint64_t)sim->k.nxl};
-    const cuuint64_t strides[3] = {16, 16 * N, 16 * N * N};
-    const cuuint32_t box[4] = {4, (cuuint32_t)lts[i], (cuuint32_t)kBoxW, (cuuint32_t)kBoxW};
-    const cuuint32_t estr[4] = {1, 1, 1, 1};
-    const CUresult rc = enc(&out[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, grid, dims, strides, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (rc != CUDA_SUCCESS) return fail(sim, "cuTensorMapEncodeTiled(grid) failed: %d", (int)rc);
-  }
-  return 0;
-}
-
 int alloc_soa(MpmSim* sim, Soa& s, size_t cap) {
-  s.stride = (cap + 31) / 32 * 32;
-  CK(cudaMalloc(&s.f, sizeof(float) * NSTREAM * s.stride));
-  CK(cudaMalloc(&s.id, sizeof(uint32_t) * s.stride));
-  CK(cudaMalloc(&s.mat, s.stride));
+  s.capacity = cap;  // multiple of kTile
+  CK(cudaMalloc(&s.f, sizeof(float) * NSTREAM * cap));
+  CK(cudaMalloc(&s.id, sizeof(uint32_t) * cap));
+  CK(cudaMalloc(&s.mat, cap));
   return 0;
 }
 void free_soa(Soa& s) {
@@ -208,18 +180,15 @@ int ensure_capacity(MpmSim* sim, size_t cap) {
     }
     cudaFree(sim->table);
     cudaFree(sim->scan_sums);
-    cudaFree(sim->tiles);
   }
+  cap = (cap + kTile - 1) / kTile * kTile;
   for (int b = 0; b < 2; ++b) {
     if (int rc = alloc_soa(sim, sim->soa[b], cap)) return rc;
-    if (int rc = make_stream_maps(sim, b)) return rc;
     CK(cudaMalloc(&sim->keys[b], sizeof(uint32_t) * cap));
     CK(cudaMalloc(&sim->vals[b], sizeof(uint32_t) * cap));
   }
-  sim->tiles_cap = cap / kTileMax + sim->n_rows + 1;  // every row adds at most one partial tile
-  CK(cudaMalloc(&sim->tiles, sizeof(TileDesc) * sim->tiles_cap));
   const size_t n_tiles = (cap + kSortTile - 1) / kSortTile;
-  sim->table_len = n_tiles * kRadix;
+  sim->table_len = n_tiles * kMaxRadix;
   CK(cudaMalloc(&sim->table, sizeof(uint32_t) * sim->table_len));
   sim->scan_sums_len = (sim->table_len + kScanTile - 1) / kScanTile;
   CK(cudaMalloc(&sim->scan_sums, sizeof(uint32_t) * sim->scan_sums_len));
@@ -237,10 +206,15 @@ int ensure_stage(MpmSim* sim, size_t n) {
   return 0;
 }
 
+const char* const kStageNames[MPM_STAGE_COUNT] = {"mpm:sort", "mpm:reset", "mpm:p2g", "mpm:grid", "mpm:g2p", "mpm:exchange"};
+
+// NVTX range per stage (visible in nsys / ncu timelines); with timing on also CUDA events + a host
+// synchronisation, which serialises the stages — profiling only
 struct StageTimer {
   MpmSim* s;
   int stage;
   StageTimer(MpmSim* s_, int st) : s(s_), stage(st) {
+    nvtxRangePushA(kStageNames[st]);
     if (s->timing) cudaEventRecord(s->ev[0], s->stream);
   }
   ~StageTimer() {
@@ -251,25 +225,42 @@ struct StageTimer {
       cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]);
       s->stage_ms[stage] += ms;
     }
+    nvtxRangePop();
   }
 };
 
+LaunchCtx make_ctx(MpmSim* sim) {
+  LaunchCtx c{};
+  c.stream = sim->stream;
+  c.n_sms = sim->n_sms;
+  c.soa = sim->soa[sim->cur];
+  c.count = sim->count;
+  c.mats_dev = sim->mats_dev;
+  c.mats_host = sim->mats_host;
+  c.n_mats = sim->n_mats;
+  c.grid = sim->grid;
+  c.k = sim->k;
+  c.diag = sim->d_diag;
+  c.p2g_mode = (int)sim->par.p2g_mode;
+  c.g2p_mode = (int)sim->par.g2p_mode;
+  c.handover_in = sim->form_ad;
+  c.tile_begin = 0;
+  c.tile_end = (sim->count + kTile - 1) / kTile;
+  return c;
+}
+
 // ---- stages -------------------------------------------------------------------------------------
-// tile descriptors of the current (freshly sorted) order, from keys[sorted_cur]
-int build_tiles(MpmSim* sim) {
-  const uint32_t* keys = sim->keys[sim->sorted_cur];
-  const uint32_t n_rows = sim->n_rows;
-  row_bounds_kernel<<<blocks_for((size_t)n_rows + 1, 256), 256, 0, sim->stream>>>(keys, (uint32_t)sim->count, (uint32_t)sim->k.N, n_rows,
-                                                                                  sim->row_first);
-  row_tiles_scan_kernel<<<1, 1024, 0, sim->stream>>>(sim->row_first, n_rows, sim->tile_base, sim->d_n_tiles);
-  CK(cudaMemsetAsync(sim->d_span, 0, 2 * sizeof(unsigned int), sim->stream));
-  tile_fill_kernel<<<blocks_for(n_rows, 256), 256, 0, sim->stream>>>(keys, sim->row_first, sim->tile_base, n_rows, sim->tiles, kLtSmall,
-                                                                     sim->d_span);
-  sim->launches += 3;
-  CK(cudaMemcpyAsync(sim->h_span, sim->d_span, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, sim->stream));
-  CK(cudaEventRecord(sim->span_ev, sim->stream));
-  sim->span_pending = true;
-  return 0;
+template <int BITS>
+void radix_pass(MpmSim* sim, int in, size_t n, int shift, int n_tiles) {
+  const size_t table_len = (size_t)n_tiles << BITS;
+  const unsigned scan_blocks = blocks_for(table_len, kScanTile);
+  radix_hist_kernel<BITS><<<n_tiles, kSortThreads, 0, sim->stream>>>(sim->keys[in], n, shift, sim->table, n_tiles);
+  scan_tile_sums_kernel<<<scan_blocks, kScanThreads, 0, sim->stream>>>(sim->table, table_len, sim->scan_sums);
+  scan_sums_kernel<<<1, 1024, 0, sim->stream>>>(sim->scan_sums, scan_blocks);
+  scan_downsweep_kernel<<<scan_blocks, kScanThreads, 0, sim->stream>>>(sim->table, table_len, sim->scan_sums);
+  radix_scatter_kernel<BITS><<<n_tiles, kSortThreads, 0, sim->stream>>>(sim->keys[in], sim->vals[in], sim->keys[in ^ 1], sim->vals[in ^ 1], n,
+                                                                       shift, sim->table, n_tiles);
+  sim->launches += 5;
 }
 
 // partial: called between the grid update and G2P, permutes only what G2P reads (sort.cuh)
@@ -282,33 +273,30 @@ int do_sort(MpmSim* sim, bool partial = false, bool keys_ready = false) {
   if (sim->d_moved) CK(cudaMemsetAsync(sim->d_moved, 0, sizeof(unsigned long long), sim->stream));
   size_t n_dead = 0;
   if (sim->comm.active()) {  // leavers out (tombstoned), arrivals appended, before the re-bin
+    // particles whose stencil left the planes held here since the last re-bin lost mass on the grid:
+    // that is a configuration error (ghost width / re-bin cadence too small for the velocities)
+    CK(cudaMemcpyAsync(sim->h_diag, sim->d_diag, sizeof(DeviceDiag), cudaMemcpyDeviceToHost, sim->stream));
+    CK(cudaMemsetAsync(&sim->d_diag->escaped, 0, sizeof(unsigned int), sim->stream));
     if (sim->comm.migrate(sim->soa[sim->cur], &sim->count, sim->capacity, sim->k, sim->stream, &sim->launches, &n_dead))
       return fail(sim, "particle migration failed: %s", sim->comm.error());
+    if (sim->h_diag->escaped)  // (migrate synchronised the stream)
+      return fail(sim, "%u particle-substeps scattered outside the %d ghost plane(s) of slab [%d,%d) since the last re-bin: "
+                       "raise MpmParams.ghost or lower sort_every", sim->h_diag->escaped, sim->ghost, sim->k.x_own_begin, sim->k.x_own_end);
   }
   const size_t n = sim->count;
-  if (n == 0) {
-    CK(cudaMemsetAsync(sim->d_n_tiles, 0, sizeof(uint32_t), sim->stream));
-    return 0;
-  }
+  if (n == 0) return 0;
   Soa& src = sim->soa[sim->cur];
-  const uint32_t dead_key = 1u << sim->key_bits;
-  const int sort_bits = sim->key_bits + (sim->comm.active() ? 1 : 0);
-  if (!keys_ready) {  // else the P2G of this substep wrote them (p2g_sched.cuh, KEYS)
+  const uint32_t dead_key = (uint32_t)sim->grid_nodes;  // behind every live key
+  const int sort_bits = sim->key_bits;
+  if (!keys_ready) {  // else the P2G of this substep wrote them (p2g_sched.cuh)
     cell_key_kernel<<<blocks_for(n, 256), 256, 0, sim->stream>>>(src, n, sim->k, sim->keys[0], sim->vals[0], dead_key);
     sim->launches++;
   }
   const int n_tiles = (int)((n + kSortTile - 1) / kSortTile);
-  const size_t table_len = (size_t)n_tiles * kRadix;
-  const unsigned scan_blocks = blocks_for(table_len, kScanTile);
+  const int bits = radix_bits(sort_bits);
   int in = 0;
-  for (int shift = 0; shift < sort_bits; shift += kRadixBits) {
-    radix_hist_kernel<<<n_tiles, kSortThreads, 0, sim->stream>>>(sim->keys[in], n, shift, sim->table, n_tiles);
-    scan_tile_sums_kernel<<<scan_blocks, kScanThreads, 0, sim->stream>>>(sim->table, table_len, sim->scan_sums);
-    scan_sums_kernel<<<1, 1024, 0, sim->stream>>>(sim->scan_sums, scan_blocks);
-    scan_downsweep_kernel<<<scan_blocks, kScanThreads, 0, sim->stream>>>(sim->table, table_len, sim->scan_sums);
-    radix_scatter_kernel<<<n_tiles, kSortThreads, 0, sim->stream>>>(sim->keys[in], sim->vals[in], sim->keys[in ^ 1],
-                                                                     sim->vals[in ^ 1], n, shift, sim->table, n_tiles);
-    sim->launches += 5;
+  for (int shift = 0; shift < sort_bits; shift += bits) {
+    if (bits == 8) radix_pass<8>(sim, in, n, shift, n_tiles); else radix_pass<9>(sim, in, n, shift, n_tiles);
     in ^= 1;
   }
   sim->sorted_cur = in;
@@ -318,63 +306,93 @@ int do_sort(MpmSim* sim, bool partial = false, bool keys_ready = false) {
   sim->launches++;
   sim->cur ^= 1;
   sim->count = n - n_dead;  // tombstones were sorted behind the live particles
-  // row tiles are needed by the fused kernel and by the shared-memory node sources of G2P only
-  if (sim->fused || !MPM_G2P_FLAT_TILES) {
-    if (int rc = build_tiles(sim)) return rc;
+  if (sim->comm.active() && sim->count) {
+    // tiles whose particles can reach the planes shared with a neighbour (drift <= ghost cells included)
+    const int g = sim->ghost;
+    const uint32_t NN = (uint32_t)sim->k.N * (uint32_t)sim->k.N;
+    const uint32_t key_lo = sim->comm.has_lo ? (uint32_t)(sim->k.x_own_begin + 2 + 2 * g - sim->k.x0) * NN : 0u;
+    const uint32_t key_hi = sim->comm.has_hi ? (uint32_t)std::max(0, sim->k.x_own_end - 2 - 2 * g - sim->k.x0) * NN : 0xffffffffu;
+    split_bounds_kernel<<<1, 32, 0, sim->stream>>>(sim->keys[in], (uint32_t)sim->count, key_lo, key_hi, sim->d_split);
+    sim->launches++;
+    CK(cudaMemcpyAsync(sim->h_split, sim->d_split, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, sim->stream));
+    CK(cudaEventRecord(sim->split_ev, sim->stream));
+    sim->split_pending = true;
+    sim->split_valid = false;
   }
   CK(cudaGetLastError());
   return 0;
 }
 
-int do_reset(MpmSim* sim, float4* grid = nullptr) {
+int do_reset(MpmSim* sim) {
   StageTimer tm(sim, MPM_STAGE_RESET);
-  CK(cudaMemsetAsync(grid ? grid : sim->grid, 0, sizeof(float4) * sim->grid_nodes, sim->stream));
+  CK(cudaMemsetAsync(sim->grid, 0, sizeof(float4) * sim->grid_nodes, sim->stream));
   return 0;
 }
 
-template <int MODEL, class O, bool EXACT, bool KEYS>
-void launch_p2g_sched_k(MpmSim* sim) {
-  const size_t n = sim->count;
-  const unsigned nbr = blocks_for(n, kP2gBlock);
-  if (sim->n_mats == 1)
-    p2g_sched_kernel<MODEL, O, EXACT, true, KEYS><<<nbr, kP2gBlock, 0, sim->stream>>>(sim->soa[sim->cur], n, sim->mats, sim->mat0, sim->grid, sim->k,
-                                                                                      sim->tm_streams[sim->cur][2], sim->keys[0], sim->vals[0]);
-  else
-    p2g_sched_kernel<MODEL, O, EXACT, false, KEYS><<<nbr, kP2gBlock, 0, sim->stream>>>(sim->soa[sim->cur], n, sim->mats, sim->mat0, sim->grid, sim->k,
-                                                                                       sim->tm_streams[sim->cur][2], sim->keys[0], sim->vals[0]);
-}
-template <int MODEL, class O, bool EXACT>
-void launch_p2g_sched(MpmSim* sim, bool keys) {
-  if (keys) launch_p2g_sched_k<MODEL, O, EXACT, true>(sim); else launch_p2g_sched_k<MODEL, O, EXACT, false>(sim);
-}
-
-// keys: also write the cell keys of the re-bin that follows in this substep; *keys_done says whether that happened
-template <int MODEL>
-int launch_p2g(MpmSim* sim, bool keys, bool* keys_done) {
-  const size_t n = sim->count;
-  Soa& p = sim->soa[sim->cur];
-  *keys_done = false;
-  if (sim->par.p2g_mode == MPM_P2G_RUNS && sim->k.N + kKeyBias <= 1023) {
-    if (sim->par.svd_mode == MPM_SVD_EXACT) launch_p2g_sched<MODEL, ExactOps, true>(sim, keys); else launch_p2g_sched<MODEL, FastOps, false>(sim, keys);
-    *keys_done = keys;
-    return 0;
-  }
-  const unsigned nb = blocks_for(n, kParticleBlock);
-  if (sim->par.svd_mode == MPM_SVD_EXACT)
-    p2g_kernel<MODEL, ExactOps, true><<<nb, kParticleBlock, 0, sim->stream>>>(p, n, sim->mats, sim->grid, sim->k);
-  else
-    p2g_kernel<MODEL, FastOps, false><<<nb, kParticleBlock, 0, sim->stream>>>(p, n, sim->mats, sim->grid, sim->k);
-  return 0;
-}
-int do_p2g(MpmSim* sim, bool keys = false, bool* keys_done = nullptr) {
-  StageTimer tm(sim, MPM_STAGE_P2G);
-  bool done = false;
+// keys: also write the cell keys of the re-bin that follows in this substep (staged kernel only);
+// *keys_done says whether that happened
+int do_p2g(MpmSim* sim, bool keys, bool* keys_done, size_t tile_begin, size_t tile_end) {
   if (keys_done) *keys_done = false;
   if (sim->count == 0) return 0;
-  if (sim->par.model == MPM_MODEL_SNOW) launch_p2g<MPM_MODEL_SNOW>(sim, keys, &done); else launch_p2g<MPM_MODEL_FIXED_COROTATED>(sim, keys, &done);
-  if (keys_done) *keys_done = done;
+  LaunchCtx c = make_ctx(sim);
+  c.tile_begin = tile_begin;
+  c.tile_end = std::min(tile_end, c.tile_end);
+  if (c.tile_begin >= c.tile_end) return 0;
+  const bool staged = sim->ops->staged && sim->par.p2g_mode == MPM_P2G_RUNS && sim->k.N <= kP2gMaxN;
+  if (keys && staged) {
+    c.sort_keys = sim->keys[0];
+    c.sort_vals = sim->vals[0];
+    if (keys_done) *keys_done = true;
+  }
+  sim->ops->p2g(c);
   sim->launches++;
   CK(cudaGetLastError());
+  return 0;
+}
+
+int do_exchange_on(MpmSim* sim, cudaStream_t stream) {
+  if (sim->comm.exchange_halo(sim->grid, sim->k, stream, &sim->launches)) return fail(sim, "halo exchange failed: %s", sim->comm.error());
+  return 0;
+}
+
+// P2G and, on slab handles, the halo exchange (partial sums of the planes shared with the
+// neighbours, comm.cuh).  The particles are sorted x-major, so those that can reach a shared plane
+// are the first and the last tiles of the SoA: they scatter first, then the exchange runs on its
+// own stream while the interior particles — which cannot touch the shared planes — scatter.
+int do_p2g_and_exchange(MpmSim* sim, bool keys, bool* keys_done) {
+  const size_t n_tiles = (sim->count + kTile - 1) / kTile;
+  if (keys_done) *keys_done = false;
+  if (!sim->comm.active()) {
+    StageTimer tm(sim, MPM_STAGE_P2G);
+    return do_p2g(sim, keys, keys_done, 0, n_tiles);
+  }
+  if (sim->split_pending && !sim->timing) {  // written at the last re-bin, long done by now
+    CK(cudaEventSynchronize(sim->split_ev));
+    sim->split_pending = false;
+    sim->split_valid = true;
+  }
+  const bool overlap = sim->split_valid && !sim->timing && getenv("MPM_NO_OVERLAP") == nullptr;
+  if (!overlap) {
+    {
+      StageTimer tm(sim, MPM_STAGE_P2G);
+      if (int rc = do_p2g(sim, keys, keys_done, 0, n_tiles)) return rc;
+    }
+    StageTimer tm(sim, MPM_STAGE_EXCHANGE);
+    return do_exchange_on(sim, sim->stream);
+  }
+  // tiles [0, a) and [b, n_tiles) hold the boundary particles
+  const size_t a = std::min<size_t>(n_tiles, ((size_t)sim->h_split[0] + kTile - 1) / kTile);
+  const size_t b = std::max<size_t>(a, std::min<size_t>(n_tiles, (size_t)sim->h_split[1] / kTile));
+  bool kd = false, kd2 = false, kd3 = false;
+  if (int rc = do_p2g(sim, keys, &kd, 0, a)) return rc;
+  if (int rc = do_p2g(sim, keys, &kd2, b, n_tiles)) return rc;
+  CK(cudaEventRecord(sim->ev_boundary, sim->stream));
+  CK(cudaStreamWaitEvent(sim->comm_stream, sim->ev_boundary, 0));
+  if (int rc = do_exchange_on(sim, sim->comm_stream)) return rc;
+  CK(cudaEventRecord(sim->ev_exchanged, sim->comm_stream));
+  if (int rc = do_p2g(sim, keys, &kd3, a, b)) return rc;
+  CK(cudaStreamWaitEvent(sim->stream, sim->ev_exchanged, 0));
+  if (keys_done) *keys_done = keys && (kd || a == 0) && (kd2 || b == n_tiles) && (kd3 || a == b);
   return 0;
 }
 
@@ -387,99 +405,19 @@ int do_grid(MpmSim* sim) {
   return 0;
 }
 
-template <int MODEL, class O, int LT, bool COUNT_MOVED>
-void launch_g2p_tile_impl(MpmSim* sim) {
-  const size_t smem = G2pTileLayout<MODEL>::bytes(LT);
-  static int per_sm = 0;  // per instantiation
-  if (!per_sm) {
-    cudaFuncSetAttribute(g2p_tile_kernel<MODEL, O, LT, COUNT_MOVED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, g2p_tile_kernel<MODEL, O, LT, COUNT_MOVED>, kG2pThreads, smem);
-    per_sm = std::max(per_sm, 1);
-  }
-  const size_t max_tiles = MPM_G2P_FLAT_TILES ? (sim->count + kTile - 1) / kTile : sim->count / kTileMax + sim->n_rows + 1;
-  const unsigned ctas = (unsigned)std::min<size_t>(max_tiles, (size_t)sim->n_sms * per_sm);
-  g2p_tile_kernel<MODEL, O, LT, COUNT_MOVED><<<ctas, kG2pThreads, smem, sim->stream>>>(
-      sim->soa[sim->cur], sim->mats, sim->mat0, sim->n_mats == 1, sim->grid, sim->k, sim->tiles, sim->d_n_tiles, sim->tm_grid[LT == kLtSmall ? 0 : 1],
-      sim->tm_streams[sim->cur][MODEL == MPM_MODEL_SNOW ? 1 : 0], sim->d_moved, sim->count, sim->d_tile_counters, sim->tile_parity);
-  sim->tile_parity ^= 1;
-}
-template <int MODEL, class O, int LT>
-void launch_g2p_tile(MpmSim* sim) {  // the cell-crossing count costs a register the default path cannot spare
-  if (sim->par.rebin_permille) launch_g2p_tile_impl<MODEL, O, LT, true>(sim); else launch_g2p_tile_impl<MODEL, O, LT, false>(sim);
-}
-
-template <int MODEL>
-int launch_g2p(MpmSim* sim) {
-  const size_t n = sim->count;
-  if (sim->par.g2p_mode == MPM_G2P_TILE) {
-    if (sim->span_pending && cudaEventQuery(sim->span_ev) == cudaSuccess) {
-      sim->span_pending = false;
-      // the small box when (nearly) every tile fits it; particles beyond the box take the
-      // global-memory gather, which is correct but slow
-      sim->tile_lt = (sim->h_span[1] && (double)sim->h_span[0] >= 0.95 * (double)sim->h_span[1]) ? kLtSmall : kLtLarge;
-    }
-    if (const char* e = getenv("MPM_TILE_LT")) sim->tile_lt = atoi(e) == kLtSmall ? kLtSmall : kLtLarge;  // experiments only
-    const bool exact = sim->par.svd_mode == MPM_SVD_EXACT;
-    if (sim->tile_lt == kLtSmall) {
-      if (exact) launch_g2p_tile<MODEL, ExactOps, kLtSmall>(sim); else launch_g2p_tile<MODEL, FastOps, kLtSmall>(sim);
-    } else {
-      if (exact) launch_g2p_tile<MODEL, ExactOps, kLtLarge>(sim); else launch_g2p_tile<MODEL, FastOps, kLtLarge>(sim);
-    }
-    return 0;
-  }
-  const unsigned nb = blocks_for(n, kG2pBlock);
-  Soa& p = sim->soa[sim->cur];
-  if (sim->par.svd_mode == MPM_SVD_EXACT)
-    g2p_kernel<MODEL, ExactOps><<<nb, kG2pBlock, 0, sim->stream>>>(p, n, sim->mats, sim->grid, sim->k);
-  else
-    g2p_kernel<MODEL, FastOps><<<nb, kG2pBlock, 0, sim->stream>>>(p, n, sim->mats, sim->grid, sim->k);
-  return 0;
-}
-int do_g2p(MpmSim* sim) {
+int do_g2p(MpmSim* sim, bool emit) {
   StageTimer tm(sim, MPM_STAGE_G2P);
+  sim->form_ad = emit;
   if (sim->count == 0) return 0;
-  if (sim->par.model == MPM_MODEL_SNOW) launch_g2p<MPM_MODEL_SNOW>(sim); else launch_g2p<MPM_MODEL_FIXED_COROTATED>(sim);
+  LaunchCtx c = make_ctx(sim);
+  c.emit = emit;
+  c.moved = sim->par.rebin_permille ? sim->d_moved : nullptr;
+  c.tile_counters = sim->d_tile_counters;
+  c.tile_parity = sim->tile_parity;
+  sim->ops->g2p(c);
+  if (sim->ops->staged && sim->par.g2p_mode == MPM_G2P_TILE) sim->tile_parity ^= 1;
   sim->launches++;
   CK(cudaGetLastError());
-  return 0;
-}
-
-template <int MODEL, class O, bool EXACT>
-void launch_g2p2g(MpmSim* sim) {
-  const size_t smem = FusedLayout<MODEL>::bytes();
-  const bool one = sim->n_mats == 1;
-  auto kern = one ? g2p2g_kernel<MODEL, O, EXACT, true> : g2p2g_kernel<MODEL, O, EXACT, false>;
-  static int per_sm[2] = {0, 0};  // per instantiation
-  if (!per_sm[one]) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[one], kern, kFusedThreads, smem);
-    per_sm[one] = std::max(per_sm[one], 1);
-  }
-  const size_t max_tiles = sim->count / kTileMax + sim->n_rows + 1;
-  const unsigned ctas = (unsigned)std::min<size_t>(max_tiles, (size_t)sim->n_sms * per_sm[one]);
-  kern<<<ctas, kFusedThreads, smem, sim->stream>>>(sim->soa[sim->cur], sim->mats, sim->mat0, sim->grid, sim->grid_b, sim->k, sim->tiles,
-                                                 sim->d_n_tiles, sim->tm_streams[sim->cur][MODEL == MPM_MODEL_SNOW ? 1 : 0]);
-}
-
-// G2P of this substep from sim->grid + P2G of the next substep into sim->grid_b (zeroed by the caller)
-int do_g2p2g(MpmSim* sim) {
-  StageTimer tm(sim, MPM_STAGE_G2P2G);
-  if (sim->count == 0) return 0;
-  const bool exact = sim->par.svd_mode == MPM_SVD_EXACT;
-  if (sim->par.model == MPM_MODEL_SNOW) {
-    if (exact) launch_g2p2g<MPM_MODEL_SNOW, ExactOps, true>(sim); else launch_g2p2g<MPM_MODEL_SNOW, FastOps, false>(sim);
-  } else {
-    if (exact) launch_g2p2g<MPM_MODEL_FIXED_COROTATED, ExactOps, true>(sim); else launch_g2p2g<MPM_MODEL_FIXED_COROTATED, FastOps, false>(sim);
-  }
-  sim->launches++;
-  CK(cudaGetLastError());
-  return 0;
-}
-
-int do_exchange(MpmSim* sim) {
-  if (!sim->comm.active()) return 0;
-  StageTimer tm(sim, MPM_STAGE_EXCHANGE);
-  if (sim->comm.exchange_halo(sim->grid, sim->k, sim->stream, &sim->launches)) return fail(sim, "halo exchange failed: %s", sim->comm.error());
   return 0;
 }
 
@@ -509,14 +447,18 @@ void mpm_make_material(double volume, double density, double E, double Nu, doubl
   out->plast_clamp_higher = (float)hi;
 }
 
-int mpm_create(const MpmParams* params, const MpmMaterial* materials, int n_materials, MpmSim** out) {
+int mpm_create_raw(const MpmParams* params, const void* materials, size_t material_bytes, int n_materials, MpmSim** out) {
   MpmSim* sim = nullptr;
   if (!params || !out) return fail(nullptr, "mpm_create: null argument");
   if (params->N < 4) return fail(nullptr, "mpm_create: N must be >= 4");
   if (n_materials < 1 || n_materials > 256 || !materials) return fail(nullptr, "mpm_create: need 1..256 materials");
-  if (params->model > MPM_MODEL_FIXED_COROTATED || params->svd_mode > MPM_SVD_FAST || params->p2g_mode > MPM_P2G_DIRECT ||
-      params->g2p_mode > MPM_G2P_DIRECT || params->fuse_mode > MPM_FUSE_G2P2G || params->rebin_permille > 1000 || params->reserved_ != 0)
-    return fail(nullptr, "mpm_create: bad model / svd_mode / p2g_mode / g2p_mode / fuse_mode");
+  if (params->svd_mode > MPM_SVD_FAST || params->p2g_mode > MPM_P2G_DIRECT || params->g2p_mode > MPM_G2P_DIRECT ||
+      params->pipeline > MPM_PIPE_CLASSIC || params->rebin_permille > 1000 || params->reserved_ != 0)
+    return fail(nullptr, "mpm_create: bad svd_mode / p2g_mode / g2p_mode / pipeline");
+  const ModelOps* ops = find_model(params->model, params->svd_mode);
+  if (!ops) return fail(nullptr, "mpm_create: no material model registered under id %u", params->model);
+  if (material_bytes != ops->material_bytes)
+    return fail(nullptr, "mpm_create: model %s takes materials of %zu bytes, caller passed %zu", ops->name, ops->material_bytes, material_bytes);
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -524,6 +466,7 @@ int mpm_create(const MpmParams* params, const MpmMaterial* materials, int n_mate
   sim = new (std::nothrow) MpmSim();
   if (!sim) return fail(nullptr, "mpm_create: out of host memory");
   sim->par = *params;
+  sim->ops = ops;
   if (params->device >= 0) {
     sim->device = params->device;
   } else {
@@ -568,34 +511,34 @@ int mpm_create(const MpmParams* params, const MpmMaterial* materials, int n_mate
   k.x0 = std::max(0, xb - sim->ghost);
   k.nxl = std::min(N, xe + 2 + sim->ghost) - k.x0;  // owned + 2 stencil planes above + ghost planes either side
   sim->grid_nodes = (size_t)k.nxl * N * N;
-  sim->n_rows = (uint32_t)k.nxl * (uint32_t)N;
-  sim->key_bits = bits_for(sim->grid_nodes);
+  if (sim->grid_nodes >= 0xffffffffull) {
+    fail(nullptr, "mpm_create: %zu grid nodes do not fit 32-bit cell keys", sim->grid_nodes);
+    mpm_destroy(sim);
+    return 1;
+  }
+  sim->key_bits = bits_for(sim->grid_nodes + (sim->whole_domain ? 0 : 1));  // slab handles: + the tombstone key
+  sim->handover = params->pipeline == MPM_PIPE_HANDOVER && ops->staged && params->p2g_mode == MPM_P2G_RUNS &&
+                  params->g2p_mode == MPM_G2P_TILE && N <= kP2gMaxN;
   CKC(cudaStreamCreateWithFlags(&sim->stream, cudaStreamNonBlocking));
   CKC(cudaEventCreate(&sim->ev[0]));
   CKC(cudaEventCreate(&sim->ev[1]));
   CKC(cudaMalloc(&sim->grid, sizeof(float4) * sim->grid_nodes));
   CKC(cudaMemsetAsync(sim->grid, 0, sizeof(float4) * sim->grid_nodes, sim->stream));
-  // the fused kernel is built from the run-based P2G and the tile-based G2P
-  sim->fused = params->fuse_mode == MPM_FUSE_G2P2G && params->p2g_mode == MPM_P2G_RUNS && params->g2p_mode == MPM_G2P_TILE &&
-               N + kKeyBias <= 1023;
-  if (sim->fused) CKC(cudaMalloc(&sim->grid_b, sizeof(float4) * sim->grid_nodes));
   sim->n_mats = n_materials;
-  sim->mat0 = materials[0];
-  CKC(cudaMalloc(&sim->mats, sizeof(MpmMaterial) * n_materials));
-  CKC(cudaMemcpy(sim->mats, materials, sizeof(MpmMaterial) * n_materials, cudaMemcpyHostToDevice));
-  CKC(cudaMalloc(&sim->d_counter, sizeof(unsigned long long)));
-  CKC(cudaMalloc(&sim->row_first, sizeof(uint32_t) * ((size_t)sim->n_rows + 1)));
-  CKC(cudaMalloc(&sim->tile_base, sizeof(uint32_t) * ((size_t)sim->n_rows + 1)));
-  CKC(cudaMalloc(&sim->d_n_tiles, sizeof(uint32_t)));
-  CKC(cudaMemsetAsync(sim->d_n_tiles, 0, sizeof(uint32_t), sim->stream));
-  if (make_grid_maps(sim, sim->grid, sim->tm_grid) || (sim->fused && make_grid_maps(sim, sim->grid_b, sim->tm_grid_b))) {
-    g_create_error = sim->err;
+  sim->mats_host = malloc(material_bytes * (size_t)n_materials);
+  if (!sim->mats_host) {
+    fail(nullptr, "mpm_create: out of host memory");
     mpm_destroy(sim);
     return 1;
   }
-  CKC(cudaMalloc(&sim->d_span, 2 * sizeof(unsigned int)));
-  CKC(cudaMallocHost(&sim->h_span, 2 * sizeof(unsigned int)));
-  CKC(cudaEventCreateWithFlags(&sim->span_ev, cudaEventDisableTiming));
+  memcpy(sim->mats_host, materials, material_bytes * (size_t)n_materials);
+  CKC(cudaMalloc(&sim->mats_dev, material_bytes * (size_t)n_materials));
+  CKC(cudaMemcpy(sim->mats_dev, materials, material_bytes * (size_t)n_materials, cudaMemcpyHostToDevice));
+  CKC(cudaMalloc(&sim->d_counter, sizeof(unsigned long long)));
+  CKC(cudaMalloc(&sim->d_diag, sizeof(DeviceDiag)));
+  CKC(cudaMemsetAsync(sim->d_diag, 0, sizeof(DeviceDiag), sim->stream));
+  CKC(cudaMallocHost(&sim->h_diag, sizeof(DeviceDiag)));
+  memset(sim->h_diag, 0, sizeof(DeviceDiag));
   CKC(cudaMalloc(&sim->d_tile_counters, 2 * sizeof(unsigned int)));
   CKC(cudaMemsetAsync(sim->d_tile_counters, 0, 2 * sizeof(unsigned int), sim->stream));
   CKC(cudaMalloc(&sim->d_moved, sizeof(unsigned long long)));
@@ -614,10 +557,21 @@ int mpm_create(const MpmParams* params, const MpmMaterial* materials, int n_mate
   return 0;
 }
 
+int mpm_create(const MpmParams* params, const MpmMaterial* materials, int n_materials, MpmSim** out) {
+  if (!params || !out) return fail(nullptr, "mpm_create: null argument");
+  if (n_materials < 1 || n_materials > 256 || !materials) return fail(nullptr, "mpm_create: need 1..256 materials");
+  const ModelOps* ops = find_model(params->model, std::min<uint32_t>(params->svd_mode, 1u));
+  if (!ops) return fail(nullptr, "mpm_create: no material model registered under id %u", params->model);
+  std::string buf(ops->material_bytes * (size_t)n_materials, '\0');
+  ops->from_abi(materials, n_materials, &buf[0]);
+  return mpm_create_raw(params, buf.data(), ops->material_bytes, n_materials, out);
+}
+
 void mpm_destroy(MpmSim* sim) {
   if (!sim) return;
   cudaSetDevice(sim->device);
   if (sim->stream) cudaStreamSynchronize(sim->stream);
+  if (sim->comm_stream) cudaStreamSynchronize(sim->comm_stream);
   sim->comm.destroy();
   for (int b = 0; b < 2; ++b) {
     free_soa(sim->soa[b]);
@@ -627,23 +581,24 @@ void mpm_destroy(MpmSim* sim) {
   cudaFree(sim->table);
   cudaFree(sim->scan_sums);
   cudaFree(sim->grid);
-  cudaFree(sim->grid_b);
-  cudaFree(sim->mats);
+  cudaFree(sim->mats_dev);
+  free(sim->mats_host);
   cudaFree(sim->aos_stage);
   cudaFree(sim->d_counter);
-  cudaFree(sim->d_span);
-  cudaFree(sim->tiles);
-  cudaFree(sim->row_first);
-  cudaFree(sim->tile_base);
-  cudaFree(sim->d_n_tiles);
+  cudaFree(sim->d_diag);
   cudaFree(sim->d_moved);
   cudaFree(sim->d_tile_counters);
+  cudaFree(sim->d_split);
+  if (sim->h_split) cudaFreeHost(sim->h_split);
+  if (sim->h_diag) cudaFreeHost(sim->h_diag);
   if (sim->h_moved) cudaFreeHost(sim->h_moved);
   if (sim->moved_ev) cudaEventDestroy(sim->moved_ev);
-  if (sim->h_span) cudaFreeHost(sim->h_span);
-  if (sim->span_ev) cudaEventDestroy(sim->span_ev);
+  if (sim->split_ev) cudaEventDestroy(sim->split_ev);
+  if (sim->ev_boundary) cudaEventDestroy(sim->ev_boundary);
+  if (sim->ev_exchanged) cudaEventDestroy(sim->ev_exchanged);
   if (sim->ev[0]) cudaEventDestroy(sim->ev[0]);
   if (sim->ev[1]) cudaEventDestroy(sim->ev[1]);
+  if (sim->comm_stream) cudaStreamDestroy(sim->comm_stream);
   if (sim->stream) cudaStreamDestroy(sim->stream);
   delete sim;
 }
@@ -658,10 +613,11 @@ static int upload_impl(MpmSim* sim, const MpmParticle* particles, size_t count, 
   sim->count = count;
   sim->first_id = 0;
   sim->cur = 0;
-  sim->grid_ready = false;
+  sim->form_ad = false;
+  CK(cudaMemsetAsync(&sim->d_diag->jp_not_one, 0, sizeof(unsigned int), sim->stream));
   if (count) {
     CK(cudaMemcpyAsync(sim->aos_stage, particles, sizeof(MpmParticle) * count, cudaMemcpyHostToDevice, sim->stream));
-    aos_to_soa_kernel<<<blocks_for(count, 256), 256, 0, sim->stream>>>(sim->aos_stage, sim->soa[0], count, 0);
+    aos_to_soa_kernel<<<blocks_for(count, 256), 256, 0, sim->stream>>>(sim->aos_stage, sim->soa[0], count, 0, 0, sim->d_diag);
     sim->launches++;
     CK(cudaGetLastError());
     if (ids) CK(cudaMemcpyAsync(sim->soa[0].id, ids, sizeof(uint32_t) * count, cudaMemcpyHostToDevice, sim->stream));
@@ -689,11 +645,10 @@ int mpm_append_particles_aos(MpmSim* sim, const MpmParticle* particles, size_t c
   if (int rc = ensure_stage(sim, count)) return rc;
   CK(cudaMemcpyAsync(sim->aos_stage, particles, sizeof(MpmParticle) * count, cudaMemcpyHostToDevice, sim->stream));
   // ids continue the upload order, so a later download returns old particles first, then these
-  aos_to_soa_kernel<<<blocks_for(count, 256), 256, 0, sim->stream>>>(sim->aos_stage, sim->soa[sim->cur], count, sim->first_id, sim->count);
+  aos_to_soa_kernel<<<blocks_for(count, 256), 256, 0, sim->stream>>>(sim->aos_stage, sim->soa[sim->cur], count, sim->first_id, sim->count, sim->d_diag);
   sim->launches++;
   CK(cudaGetLastError());
   sim->count += count;
-  sim->grid_ready = false;
   return do_sort(sim);
 }
 
@@ -732,7 +687,8 @@ int mpm_download_positions(MpmSim* sim, float* xyz, size_t capacity, size_t* cou
   return 0;
 }
 
-int mpm_generate_dense_block(MpmSim* sim, uint64_t first_id, uint64_t count, uint32_t seed, float lo, float hi, uint8_t material) {
+int mpm_generate_dense_block_stressed(MpmSim* sim, uint64_t first_id, uint64_t count, uint32_t seed, float lo, float hi, uint8_t material,
+                                      float shear, float f_noise) {
   if (!sim) return 1;
   CK(cudaSetDevice(sim->device));
   const bool whole = sim->whole_domain;
@@ -742,12 +698,13 @@ int mpm_generate_dense_block(MpmSim* sim, uint64_t first_id, uint64_t count, uin
     return fail(sim, "mpm_generate_dense_block: slab handles need MpmParams.capacity");
   }
   sim->cur = 0;
-  sim->grid_ready = false;
+  sim->form_ad = false;
   sim->first_id = (uint32_t)first_id;
   CK(cudaMemsetAsync(sim->d_counter, 0, sizeof(unsigned long long), sim->stream));
+  CK(cudaMemsetAsync(&sim->d_diag->jp_not_one, 0, sizeof(unsigned int), sim->stream));
   if (count) {
-    generate_block_kernel<<<blocks_for(count, 256), 256, 0, sim->stream>>>(sim->soa[0], first_id, count, lowbias32(seed), lo, hi,
-                                                                            material, sim->k, whole, sim->d_counter, sim->capacity);
+    generate_block_kernel<<<blocks_for(count, 256), 256, 0, sim->stream>>>(sim->soa[0], first_id, count, lowbias32(seed), lo, hi, material,
+                                                                            sim->k, whole, sim->d_counter, sim->capacity, BlockStress{shear, f_noise});
     sim->launches++;
     CK(cudaGetLastError());
   }
@@ -762,6 +719,9 @@ int mpm_generate_dense_block(MpmSim* sim, uint64_t first_id, uint64_t count, uin
   }
   return do_sort(sim);
 }
+int mpm_generate_dense_block(MpmSim* sim, uint64_t first_id, uint64_t count, uint32_t seed, float lo, float hi, uint8_t material) {
+  return mpm_generate_dense_block_stressed(sim, first_id, count, seed, lo, hi, material, 0.0f, 0.0f);
+}
 
 size_t mpm_particle_count(const MpmSim* sim) { return sim ? sim->count : 0; }
 size_t mpm_grid_nodes(const MpmSim* sim) { return sim ? sim->grid_nodes : 0; }
@@ -771,22 +731,21 @@ uint64_t mpm_kernel_launches(const MpmSim* sim) { return sim ? sim->launches : 0
 uint64_t mpm_rebins_done(const MpmSim* sim) { return sim ? sim->rebins : 0; }
 void* mpm_stream(MpmSim* sim) { return sim ? (void*)sim->stream : nullptr; }
 
+// single stages, for parity tests and profiling: the same kernels mpm_advance runs, on particles in
+// the reference's form (C, not the handed-over affine matrix)
 int mpm_stage_sort(MpmSim* sim) { if (!sim) return 1; CK(cudaSetDevice(sim->device)); return do_sort(sim); }
-// the single stages work on the primary grid with the separate kernels and leave the fused
-// pipeline's look-ahead grid invalid (mpm_advance rebuilds it)
-int mpm_stage_reset_grid(MpmSim* sim) { if (!sim) return 1; CK(cudaSetDevice(sim->device)); sim->grid_ready = false; return do_reset(sim); }
-int mpm_stage_p2g(MpmSim* sim) { if (!sim) return 1; CK(cudaSetDevice(sim->device)); sim->grid_ready = false; return do_p2g(sim); }
-int mpm_stage_grid_update(MpmSim* sim) { if (!sim) return 1; CK(cudaSetDevice(sim->device)); sim->grid_ready = false; return do_grid(sim); }
-int mpm_stage_g2p(MpmSim* sim) { if (!sim) return 1; CK(cudaSetDevice(sim->device)); sim->grid_ready = false; return do_g2p(sim); }
+int mpm_stage_reset_grid(MpmSim* sim) { if (!sim) return 1; CK(cudaSetDevice(sim->device)); return do_reset(sim); }
+int mpm_stage_p2g(MpmSim* sim) { if (!sim) return 1; CK(cudaSetDevice(sim->device)); return do_p2g_and_exchange(sim, false, nullptr); }
+int mpm_stage_grid_update(MpmSim* sim) { if (!sim) return 1; CK(cudaSetDevice(sim->device)); return do_grid(sim); }
+int mpm_stage_g2p(MpmSim* sim) { if (!sim) return 1; CK(cudaSetDevice(sim->device)); return do_g2p(sim, false); }
 
 int mpm_advance(MpmSim* sim, int n_substeps) {
   if (!sim) return 1;
   CK(cudaSetDevice(sim->device));
   for (int s = 0; s < n_substeps; ++s) {
-    bool rebin_late = false;
     bool due = sim->par.sort_every && sim->steps_since_sort >= sim->par.sort_every;
     // (not for slab handles: every rank must reach the migration of a re-bin in the same substep)
-    const bool adaptive = sim->par.rebin_permille && !sim->fused && sim->par.g2p_mode == MPM_G2P_TILE && !sim->comm.active();
+    const bool adaptive = sim->par.rebin_permille && sim->ops->staged && sim->par.g2p_mode == MPM_G2P_TILE && !sim->comm.active();
     if (adaptive) {
       // re-bin on measured disorder: the count of cell crossings since the last re-bin arrives a
       // substep or two late (asynchronous read-back), which is early enough for a locality heuristic
@@ -799,49 +758,26 @@ int mpm_advance(MpmSim* sim, int n_substeps) {
       }
       due = due || (sim->steps_since_sort > 0 && sim->moved_seen * 1000ull >= (unsigned long long)sim->par.rebin_permille * sim->count && sim->count > 0);
     }
-    if (due) {
-      // (slab handles migrate whole particle records at the re-bin: v and C are still the previous
-      // substep's there, so leavers carry a complete state; the fused pipeline has no such gap)
-      rebin_late = !sim->fused;
-      if (!rebin_late) {
-        if (int rc = do_sort(sim)) return rc;
-      }
+    if (due) {  // the keys P2G writes come with fresh out-of-domain / non-finite counts
+      CK(cudaMemsetAsync(&sim->d_diag->nonfinite, 0, 2 * sizeof(unsigned int), sim->stream));
     }
-    if (sim->fused) {
-      // `grid` = velocities of this substep (built here on the first substep after the particles
-      // changed, otherwise left by the previous fused kernel); the fused kernel gathers from it
-      // and scatters the next substep into grid_b, which then becomes `grid`.
-      if (!sim->grid_ready) {
-        if (int rc = do_reset(sim)) return rc;
-        if (int rc = do_p2g(sim)) return rc;
-        if (int rc = do_exchange(sim)) return rc;
-        if (int rc = do_grid(sim)) return rc;
-      }
-      if (int rc = do_reset(sim, sim->grid_b)) return rc;
-      if (int rc = do_g2p2g(sim)) return rc;
-      std::swap(sim->grid, sim->grid_b);
-      for (int i = 0; i < 2; ++i) std::swap(sim->tm_grid[i], sim->tm_grid_b[i]);
-      if (int rc = do_exchange(sim)) return rc;
-      if (int rc = do_grid(sim)) return rc;
-      sim->grid_ready = true;
-    } else {
-      bool keys_ready = false;  // slab handles tombstone leavers at the re-bin, which changes their keys
-      if (int rc = do_reset(sim)) return rc;
-      if (int rc = do_p2g(sim, rebin_late && !sim->comm.active(), &keys_ready)) return rc;
-      if (int rc = do_exchange(sim)) return rc;
-      if (int rc = do_grid(sim)) return rc;
-      // a due re-bin runs here when it can: G2P is about to overwrite v and C, so only x, F, Jp
-      // have to move (the keys come from the positions this substep started with)
-      if (rebin_late) {
-        if (int rc = do_sort(sim, true, keys_ready)) return rc;
-      }
-      if (int rc = do_g2p(sim)) return rc;
-      if (adaptive && !sim->moved_pending) {
-        CK(cudaMemcpyAsync(sim->h_moved, sim->d_moved, sizeof(unsigned long long), cudaMemcpyDeviceToHost, sim->stream));
-        CK(cudaEventRecord(sim->moved_ev, sim->stream));
-        sim->moved_pending = true;
-        sim->moved_issued_at = sim->substeps;
-      }
+    bool keys_ready = false;  // slab handles tombstone leavers at the re-bin, which changes their keys
+    if (int rc = do_reset(sim)) return rc;
+    if (int rc = do_p2g_and_exchange(sim, due && !sim->comm.active(), &keys_ready)) return rc;
+    if (int rc = do_grid(sim)) return rc;
+    // a due re-bin runs here: G2P is about to overwrite v and C, so only x, F, Jp have to move (the
+    // keys come from the positions this substep started with).  Slab handles migrate whole particle
+    // records at this point; the new owner's G2P needs x, F, Jp only.
+    if (due) {
+      if (int rc = do_sort(sim, true, keys_ready)) return rc;
+    }
+    // hand-over: every G2P but the last of this call leaves the next P2G's affine matrix in the C rows
+    if (int rc = do_g2p(sim, sim->handover && s + 1 < n_substeps)) return rc;
+    if (adaptive && !sim->moved_pending) {
+      CK(cudaMemcpyAsync(sim->h_moved, sim->d_moved, sizeof(unsigned long long), cudaMemcpyDeviceToHost, sim->stream));
+      CK(cudaEventRecord(sim->moved_ev, sim->stream));
+      sim->moved_pending = true;
+      sim->moved_issued_at = sim->substeps;
     }
     sim->t += (double)sim->par.dt;
     sim->substeps++;
@@ -869,7 +805,6 @@ int mpm_debug_upload_grid(MpmSim* sim, const float* vec4, size_t n_nodes) {
   if (!sim || !vec4) return 1;
   CK(cudaSetDevice(sim->device));
   if (n_nodes != sim->grid_nodes) return fail(sim, "grid has %zu nodes, caller passed %zu", sim->grid_nodes, n_nodes);
-  sim->grid_ready = false;
   CK(cudaMemcpyAsync(sim->grid, vec4, sizeof(float4) * n_nodes, cudaMemcpyHostToDevice, sim->stream));
   CK(cudaStreamSynchronize(sim->stream));
   return 0;
@@ -879,10 +814,9 @@ int mpm_debug_overwrite_particles_aos(MpmSim* sim, const MpmParticle* particles,
   CK(cudaSetDevice(sim->device));
   if (count != sim->count || !sim->whole_domain) return fail(sim, "overwrite needs the same particle count on a whole-domain handle");
   if (count == 0) return 0;
-  sim->grid_ready = false;
   if (int rc = ensure_stage(sim, count)) return rc;
   CK(cudaMemcpyAsync(sim->aos_stage, particles, sizeof(MpmParticle) * count, cudaMemcpyHostToDevice, sim->stream));
-  aos_overwrite_kernel<<<blocks_for(count, 256), 256, 0, sim->stream>>>(sim->aos_stage, sim->soa[sim->cur], count, sim->first_id);
+  aos_overwrite_kernel<<<blocks_for(count, 256), 256, 0, sim->stream>>>(sim->aos_stage, sim->soa[sim->cur], count, sim->first_id, sim->d_diag);
   sim->launches++;
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(sim->stream));
@@ -908,28 +842,53 @@ int mpm_get_stage_times(MpmSim* sim, float ms[MPM_STAGE_COUNT]) {
   }
   return 0;
 }
+int mpm_set_stage_timing(MpmSim* sim, int on) {
+  if (!sim) return 1;
+  sim->timing = on != 0;
+  return 0;
+}
+int mpm_get_diagnostics(MpmSim* sim, MpmDiagnostics* out) {
+  if (!sim || !out) return 1;
+  CK(cudaSetDevice(sim->device));
+  static_assert(sizeof(MpmDiagnostics) == sizeof(DeviceDiag), "same four counters");
+  CK(cudaMemcpyAsync(sim->h_diag, sim->d_diag, sizeof(DeviceDiag), cudaMemcpyDeviceToHost, sim->stream));
+  CK(cudaStreamSynchronize(sim->stream));
+  memcpy(out, sim->h_diag, sizeof(DeviceDiag));
+  return 0;
+}
 
 int mpm_comm_unique_id(void* id128) { return Comm::unique_id(id128); }
 int mpm_attach_comm(MpmSim* sim, const void* id128, int rank, int nranks) {
   if (!sim) return 1;
   CK(cudaSetDevice(sim->device));
   if (sim->capacity == 0) return fail(sim, "mpm_attach_comm: set MpmParams.capacity for slab handles");
+  if (sim->par.sort_every == 0)
+    return fail(sim, "mpm_attach_comm: slab handles migrate particles at the re-bin, sort_every = 0 would never migrate");
   if (sim->comm.init(id128, rank, nranks, sim->k, sim->ghost, sim->capacity, sim->stream)) return fail(sim, "mpm_attach_comm: %s", sim->comm.error());
+  int lo = 0, hi = 0;
+  CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  CK(cudaStreamCreateWithPriority(&sim->comm_stream, cudaStreamNonBlocking, hi));
+  CK(cudaEventCreateWithFlags(&sim->ev_boundary, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&sim->ev_exchanged, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&sim->split_ev, cudaEventDisableTiming));
+  CK(cudaMalloc(&sim->d_split, 2 * sizeof(uint32_t)));
+  CK(cudaMallocHost(&sim->h_split, 2 * sizeof(uint32_t)));
   return 0;
 }
 
 // ---- linalg hooks ---------------------------------------------------------------------------------
-static int linalg_run(const float* A, size_t n, int mode, int what, float* o0, float* o1, float* o2) {
+static int linalg_run(const float* A, size_t n, int mode, int what, float* o0, float* o1, float* o2, float aux0 = 0.f, float aux1 = 0.f) {
   MpmSim* sim = nullptr;
   float *dA = nullptr, *d0 = nullptr, *d1 = nullptr, *d2 = nullptr;
+  const size_t in_sz = (what == 3) ? 3 * n : 9 * n;
   const size_t sz0 = (what == 2) ? n : 9 * n;
-  CK(cudaMalloc(&dA, sizeof(float) * 9 * n));
+  CK(cudaMalloc(&dA, sizeof(float) * in_sz));
   CK(cudaMalloc(&d0, sizeof(float) * sz0));
   if (what == 0) {
     CK(cudaMalloc(&d1, sizeof(float) * 3 * n));
     CK(cudaMalloc(&d2, sizeof(float) * 9 * n));
   }
-  CK(cudaMemcpy(dA, A, sizeof(float) * 9 * n, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dA, A, sizeof(float) * in_sz, cudaMemcpyHostToDevice));
   const unsigned nb = blocks_for(n, 128);
   if (what == 0) {
     if (mode == MPM_SVD_EXACT) svd3_batch_kernel<ExactOps><<<nb, 128>>>(dA, d0, d1, d2, n);
@@ -937,8 +896,10 @@ static int linalg_run(const float* A, size_t n, int mode, int what, float* o0, f
   } else if (what == 1) {
     if (mode == MPM_SVD_EXACT) polar_batch_kernel<ExactOps><<<nb, 128>>>(dA, d0, n);
     else polar_batch_kernel<FastOps><<<nb, 128>>>(dA, d0, n);
-  } else {
+  } else if (what == 2) {
     det_batch_kernel<<<nb, 128>>>(dA, d0, n);
+  } else {
+    dinv_batch_kernel<<<nb, 128>>>(dA, d0, n, aux0, aux1);
   }
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
@@ -964,6 +925,12 @@ int mpm_polar_batch(const float* A, float* R, size_t n, int svd_mode) {
 int mpm_determinant_batch(const float* A, float* det, size_t n) {
   if (!n) return 0;
   return linalg_run(A, n, 0, 2, det, nullptr, nullptr);
+}
+int mpm_dinv_batch(const float* xyz, float* Dinv9, size_t n, uint32_t N) {
+  if (!n) return 0;
+  const float dx = (float)(1.0 / (double)N);
+  const float dx_inv = (float)(1.0 / (double)dx);
+  return linalg_run(xyz, n, 0, 3, Dinv9, nullptr, nullptr, dx, dx_inv);
 }
 
 }  // extern "C"

@@ -15,8 +15,12 @@ constexpr int kSortThreads = 256;
 constexpr int kSortWarps = kSortThreads / 32;
 constexpr int kSortItems = 8;                                     // keys per thread
 constexpr int kSortTile = kSortThreads * kSortItems;              // keys per block
-constexpr int kRadixBits = 8;
-constexpr int kRadix = 1 << kRadixBits;
+// digit width per pass: 8 bits unless 9 bits save a whole pass (slab handles at N = 512 have 25-bit keys
+// plus the tombstone key: 3 passes of 9 instead of 4 of 8)
+constexpr int kMaxRadixBits = 9;
+constexpr int kMaxRadix = 1 << kMaxRadixBits;
+inline int radix_passes(int key_bits) { return (key_bits + kMaxRadixBits - 1) / kMaxRadixBits; }
+inline int radix_bits(int key_bits) { return ((key_bits + 7) / 8 > radix_passes(key_bits)) ? 9 : 8; }
 
 // key = N^2*bi + N*bj + bk of the clamped base node, bi local to the slab
 // tombstoned particles (migrated away) get dead_key, which sorts behind every live key
@@ -29,11 +33,12 @@ __global__ void cell_key_kernel(Soa p, size_t count, KParams k, uint32_t* __rest
     keys[i] = dead_key;
     return;
   }
+  const float* c = p.col(i);
   int b[3];
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
     float fx, w[3];
-    bspline(p.s(SX + a)[i], k.dx_inv, b[a], fx, w);
+    bspline(c[(SX + a) * kTile], k.dx_inv, b[a], fx, w);
     b[a] = min(max(b[a], 0), k.N - 1);
   }
   const int bx = min(max(b[0] - k.x0, 0), k.nxl - 1);
@@ -41,8 +46,10 @@ __global__ void cell_key_kernel(Soa p, size_t count, KParams k, uint32_t* __rest
 }
 
 // (a) table[d * n_tiles + tile] = number of keys of this tile whose digit is d
+template <int BITS>
 __global__ void __launch_bounds__(kSortThreads)
 radix_hist_kernel(const uint32_t* __restrict__ keys, size_t count, int shift, uint32_t* __restrict__ table, int n_tiles) {
+  constexpr int kRadix = 1 << BITS;
   __shared__ uint32_t h[kRadix];
   for (int d = threadIdx.x; d < kRadix; d += kSortThreads) h[d] = 0;
   __syncthreads();
@@ -144,9 +151,11 @@ __global__ void __launch_bounds__(kScanThreads) scan_downsweep_kernel(uint32_t* 
 #ifndef MPM_SCATTER_MINBLK
 #define MPM_SCATTER_MINBLK 5
 #endif
-__global__ void __launch_bounds__(kSortThreads, MPM_SCATTER_MINBLK)
+template <int BITS>
+__global__ void __launch_bounds__(kSortThreads, BITS == 8 ? MPM_SCATTER_MINBLK : 4)
 radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ keys_out,
                      uint32_t* __restrict__ vals_out, size_t count, int shift, const uint32_t* __restrict__ table, int n_tiles) {
+  constexpr int kRadix = 1 << BITS;
   __shared__ uint32_t cnt[kSortWarps][kRadix];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int d = threadIdx.x; d < kSortWarps * kRadix; d += kSortThreads) (&cnt[0][0])[d] = 0;
@@ -203,37 +212,50 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
 static_assert(kSortTile == kSortWarps * kSortItems * 32, "tile layout");
 
 // SoA permute: dst[r] = src[perm[r]] for every stream (+ id, material).
-// PARTIAL: only what G2P reads (x, F, Jp = stream rows 0..12, + id, material) — for a re-bin placed
+// PARTIAL: only what G2P reads (x, F, Jp = stream rows SX..SJ, + id, material) — for a re-bin placed
 // between the grid update and G2P, which overwrites v and C of every particle it processes.  The
 // particles G2P leaves untouched (whole stencil outside the domain, src/mpm.cu:128-132) keep all
 // their streams.  58 % of the full permute's bytes.
 template <bool PARTIAL>
 __global__ void __launch_bounds__(256) permute_kernel(Soa src, Soa dst, const uint32_t* __restrict__ perm, size_t count, KParams k) {
-  static_assert(SX == 0 && SF == 3 && SJ == 12 && SV == 13, "rows 0..12 = x, F, Jp");
-  constexpr int NROWS = PARTIAL ? SV : NSTREAM;
+  static_assert(SX == 12 && SJ == NSTREAM - 1, "rows SX.. = x, F, Jp");
+  constexpr int R0 = PARTIAL ? SX : 0;
   const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= count) return;
   const uint32_t s = perm[r];
-  float t[NROWS];
+  const float* __restrict__ in = src.col(s);
+  float* __restrict__ out = dst.tile(blockIdx.x) + threadIdx.x;
+  float t[NSTREAM - R0];
 #pragma unroll
-  for (int q = 0; q < NROWS; ++q) t[q] = src.s(q)[s];
+  for (int q = R0; q < NSTREAM; ++q) t[q - R0] = in[q * kTile];
   const uint32_t id = src.id[s];
   const uint8_t mt = src.mat[s];
 #pragma unroll
-  for (int q = 0; q < NROWS; ++q) dst.s(q)[r] = t[q];
+  for (int q = R0; q < NSTREAM; ++q) out[q * kTile] = t[q - R0];
   dst.id[r] = id;
   dst.mat[r] = mt;
   if (PARTIAL) {
-    bool untouched = false;
+    int base[3];
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      const int base = (int)(t[SX + a] * k.dx_inv - 0.5f);
-      untouched = untouched || (base + 3 < 0 || base >= k.N);
-    }
-    if (untouched) {
-      for (int q = NROWS; q < NSTREAM; ++q) dst.s(q)[r] = src.s(q)[s];
+    for (int a = 0; a < 3; ++a) base[a] = (int)(t[SX - R0 + a] * k.dx_inv - 0.5f);
+    if (stencil_outside(base, k.N)) {
+      for (int q = 0; q < R0; ++q) out[q * kTile] = in[q * kTile];
     }
   }
+}
+
+// out[0] = first sorted position whose key >= key_lo, out[1] = first whose key >= key_hi (slab handles:
+// the particles before out[0] / from out[1] on can reach the planes shared with a neighbour)
+__global__ void split_bounds_kernel(const uint32_t* __restrict__ keys, uint32_t count, uint32_t key_lo, uint32_t key_hi,
+                                    uint32_t* __restrict__ out) {
+  if (threadIdx.x >= 2) return;
+  const uint32_t target = threadIdx.x == 0 ? key_lo : key_hi;
+  uint32_t lo = 0, hi = count;
+  while (lo < hi) {
+    const uint32_t mid = lo + ((hi - lo) >> 1);
+    if (keys[mid] < target) lo = mid + 1; else hi = mid;
+  }
+  out[threadIdx.x] = lo;
 }
 
 }  // namespace mpm

@@ -406,15 +406,16 @@ inline void weights_per_direction(const float x[3], float dx_inv, int base[3], f
 // D_inv_const, InterpolationKernel.cuh:71-73: Identity * 4.0 * dx_inv * dx_inv (scalar promoted to f32).
 inline float dinv_scalar(float dx_inv) { return (4.0f * dx_inv) * dx_inv; }
 
-enum ModelKind { kSnow = 0, kFixedCorotated = 1 };
+enum ModelKind { kSnow = 0, kFixedCorotated = 1, kJelly = 2 };
 
-// MMSnow::computePF, include/MaterialModel.cuh:85-93; MMFixedCorotated::computePF, :56-61.
+// MMSnow::computePF, include/MaterialModel.cuh:85-93; MMFixedCorotated::computePF, :56-61;
+// MMJelly::computePF, :133-140 (the same expression as MMSnow's).
 inline M3 computePF(const M3& F, float Jp, const Material& m, int kind) {
   M3 R, Sym;
   polar(F, R, Sym);
   float mu = m.mu0, lambda = m.lambda0;
-  if (kind == kSnow) {
-    float e = (float)std::exp((double)m.hardening * (1.0 - (double)Jp));  // :88
+  if (kind == kSnow || kind == kJelly) {
+    float e = (float)std::exp((double)m.hardening * (1.0 - (double)Jp));  // :88, :136
     mu = m.mu0 * e;
     lambda = m.lambda0 * e;
   }
@@ -428,8 +429,14 @@ inline M3 computePF(const M3& F, float Jp, const Material& m, int kind) {
   return PF;
 }
 
-// MMSnow::endOfStepMutation, include/MaterialModel.cuh:95-114 (no-op for MMFixedCorotated, :63).
+// MMSnow::endOfStepMutation, include/MaterialModel.cuh:95-114 (no-op for MMFixedCorotated, :63);
+// MMJelly::endOfStepMutation, :142-149: Jp * det F / det F of the SAME F, then the clamp.
 inline void endOfStepMutation(M3& F, float& Jp, const Material& m, int kind) {
+  if (kind == kJelly) {
+    float oldJ = determinant(F);
+    Jp = clampf(Jp * oldJ / determinant(F), 0.6f, 20.0f);
+    return;
+  }
   if (kind != kSnow) return;
   M3 U, V;
   float sig[3];

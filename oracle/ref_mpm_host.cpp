@@ -6,7 +6,7 @@
 // compiled against the Eigen shim in oracle/shim (Eigen itself is not in this image), with the
 // CUDA execution model replaced by a serial loop: one call of the kernel function per
 // (blockIdx, threadIdx).  Nothing from the reference is copied into the repository; the .inc
-// files live in a temporary directory during the build only.  Result: oracle/_ref/libref_mpm_{snow,fc}.so, the
+// files live in a temporary directory during the build only.  Result: oracle/_ref/libref_mpm_{snow,fc,jelly}.so, the
 // "reference itself run here" that pins oracle/mpm_oracle.cpp (tests/test_oracle.py).
 // Caveats (documented in DESIGN.md): host float arithmetic without FMA contraction, whereas the
 // reference's nvcc build contracts; the kernels are launched only for particle counts <= N^3
@@ -64,9 +64,12 @@ namespace linalg {
 }
 
 // the four aliases of include/mpm.cuh:24-27 (that header itself needs boost/libigl/GL)
-#ifdef REF_FIXED_COROTATED
+#if defined(REF_FIXED_COROTATED)
 using Particle = MLS_APIC_Particle;
 using MaterialModel = MMFixedCorotated<Particle>;
+#elif defined(REF_JELLY)
+using Particle = MLS_APIC_Particle;
+using MaterialModel = MMJelly<Particle>;
 #else
 using Particle = MLS_APIC_Particle;
 using MaterialModel = MMSnow<Particle>;
@@ -84,8 +87,10 @@ std::vector<MaterialModel> make_models(const float* mats7, int n) {
   std::vector<MaterialModel> v;
   for (int i = 0; i < n; ++i) {
     const float* m = mats7 + 7 * i;
-#ifdef REF_FIXED_COROTATED
+#if defined(REF_FIXED_COROTATED)
     MaterialModel mm(m[0], 1.0f, 1.0f, 0.25f);
+#elif defined(REF_JELLY)
+    MaterialModel mm(m[0], 1.0f, 1.0f, 0.25f, m[4]);
 #else
     MaterialModel mm(m[0], 1.0f, 1.0f, 0.25f, m[4], m[5], m[6]);
 #endif
@@ -99,8 +104,10 @@ std::vector<MaterialModel> make_models(const float* mats7, int n) {
 }
 }  // namespace
 
-#ifdef REF_FIXED_COROTATED
+#if defined(REF_FIXED_COROTATED)
 #define REFNAME(x) ref_fc_##x
+#elif defined(REF_JELLY)
+#define REFNAME(x) ref_jelly_##x
 #else
 #define REFNAME(x) ref_snow_##x
 #endif
@@ -113,9 +120,13 @@ size_t REFNAME(sizeof_material)() { return sizeof(MaterialModel); }
 // MaterialModel constructor exactly as src/main.cu:36-42 calls it (snow build only)
 void REFNAME(make_material)(double volume, double density, double E, double Nu, double hardening, double lo,
                             double hi, float* out7) {
-#ifdef REF_FIXED_COROTATED
+#if defined(REF_FIXED_COROTATED)
   MaterialModel mm(volume, density, E, Nu);
   float tmp[7] = {mm.particleVolume, mm.particleMass, mm.mu0, mm.lambda0, (float)hardening, (float)lo, (float)hi};
+  std::memcpy(out7, tmp, sizeof(tmp));
+#elif defined(REF_JELLY)
+  MaterialModel mm(volume, density, E, Nu, hardening);
+  float tmp[7] = {mm.particleVolume, mm.particleMass, mm.mu0, mm.lambda0, mm.hardening, (float)lo, (float)hi};
   std::memcpy(out7, tmp, sizeof(tmp));
 #else
   MaterialModel mm(volume, density, E, Nu, hardening, lo, hi);

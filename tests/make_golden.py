@@ -27,7 +27,7 @@ def svd3_golden():
 
 
 def substep_golden():
-    for kind, name in ((ol.SNOW, "snow"), (ol.FIXED_COROTATED, "fc")):
+    for kind, name in ((ol.SNOW, "snow"), (ol.FIXED_COROTATED, "fc"), (ol.JELLY, "jelly")):
         ref = ol.Ref(kind)
         assert ref.available, "needs oracle/_ref (build where /root/reference is mounted)"
         N, dt = 16, 1e-4

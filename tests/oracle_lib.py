@@ -19,7 +19,7 @@ PARTICLE_DTYPE = np.dtype(
 )
 assert PARTICLE_DTYPE.itemsize == 104
 
-SNOW, FIXED_COROTATED = 0, 1
+SNOW, FIXED_COROTATED, JELLY = 0, 1, 2
 
 _fp = ctypes.POINTER(ctypes.c_float)
 _u32p = ctypes.POINTER(ctypes.c_uint32)
@@ -175,8 +175,9 @@ class Ref:
 
     def __init__(self, kind):
         self.kind = kind
-        self.pre = "ref_snow_" if kind == SNOW else "ref_fc_"
-        self.lib = ref_lib("libref_mpm_snow" if kind == SNOW else "libref_mpm_fc")
+        tag = {SNOW: "snow", FIXED_COROTATED: "fc", JELLY: "jelly"}[kind]
+        self.pre = f"ref_{tag}_"
+        self.lib = ref_lib("libref_mpm_" + tag)
         self.available = self.lib is not None
 
     def fn(self, name):

@@ -17,9 +17,10 @@ def two_spheres(N=32, density=500000.0, seed=1, kind=ol.SNOW, perturb=True):
         p["Jp"] = 1.0 + 0.05 * rng.standard_normal(len(p)).astype(np.float32)
     if kind == ol.SNOW:
         mats = ol.make_material(1.0 / density)  # scenes/snowman.toml
-    else:
+    elif kind == ol.JELLY:
+        mats = ol.make_material(1.0 / density, 1000.0, 1.0e5, 0.3, 10.0, 0.0, 1e30)  # MMJelly's defaults
+    else:  # fixed-corotated keeps the perturbed Jp: its lambda term reads it (MaterialModel.cuh:59-60)
         mats = ol.make_material(1.0 / density, 1000.0, 1.4e5, 0.2, 0.0, 0.0, 1e30)
-        p["Jp"] = 1.0
     return p, mats
 
 

@@ -19,7 +19,7 @@ def _two_gpus():
     return torch.cuda.device_count() >= 2
 
 
-def _run_ranks(N, mats, kind, p, slabs, steps, sort_every, mode=0, fuse_mode=0):
+def _run_ranks(N, mats, kind, p, slabs, steps, sort_every, mode=0, pipeline=0):
     import mpm_b200
     from mpm_b200 import slabs as sl
 
@@ -31,7 +31,7 @@ def _run_ranks(N, mats, kind, p, slabs, steps, sort_every, mode=0, fuse_mode=0):
         try:
             xb, xe = slabs[r]
             sim = mpm_b200.Sim(N, DT, mats, model=kind, svd_mode=mode, sort_every=sort_every, x_begin=xb, x_end=xe,
-                               device=r, capacity=len(p), fuse_mode=fuse_mode)
+                               device=r, capacity=len(p), pipeline=pipeline)
             sim.attach_comm(uid, r, len(slabs))
             mine = np.where(own == r)[0]
             sim.upload_with_ids(np.ascontiguousarray(p[mine]), mine.astype(np.uint32))
@@ -57,8 +57,8 @@ def _run_ranks(N, mats, kind, p, slabs, steps, sort_every, mode=0, fuse_mode=0):
 
 
 @pytest.mark.parametrize("kind", [ol.SNOW, ol.FIXED_COROTATED])
-@pytest.mark.parametrize("fuse_mode", [0, 1])  # separate kernels (default) / fused G2P2G pipeline
-def test_two_slabs_match_single_gpu_and_oracle(kind, fuse_mode):
+@pytest.mark.parametrize("pipeline", [0, 1])  # hand-over (default) / classic
+def test_two_slabs_match_single_gpu_and_oracle(kind, pipeline):
     if not _two_gpus():
         pytest.skip("needs 2 GPUs")
     import mpm_b200
@@ -66,7 +66,7 @@ def test_two_slabs_match_single_gpu_and_oracle(kind, fuse_mode):
     N, steps = 32, 60
     p, mats = scenes.two_spheres(N, kind=kind, perturb=False)
     p["v"][:, 0] += 2.0  # drift across the slab boundary at x = 0.5 -> exercises migration
-    merged, counts = _run_ranks(N, mats, kind, p, [(0, 16), (16, 32)], steps, sort_every=5, fuse_mode=fuse_mode)
+    merged, counts = _run_ranks(N, mats, kind, p, [(0, 16), (16, 32)], steps, sort_every=5, pipeline=pipeline)
     single = mpm_b200.Sim(N, DT, mats, model=kind, sort_every=5)
     single.upload(p)
     single.advance(steps)

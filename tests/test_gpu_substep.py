@@ -144,17 +144,21 @@ def test_g2p_single_step_from_identical_grid(kind, mode, g2p_mode):
 
 @pytest.mark.parametrize("kind,steps", [(ol.SNOW, 100), (ol.FIXED_COROTATED, 100)])
 @pytest.mark.parametrize("mode", MODES)
-@pytest.mark.parametrize("sort_every,g2p_mode,fuse_mode", [(10, 0, 0), (0, 0, 0), (10, 0, 1), (0, 0, 1), (10, 1, 0)])
-def test_short_horizon_against_oracle(kind, steps, mode, sort_every, g2p_mode, fuse_mode):
+@pytest.mark.parametrize("sort_every,g2p_mode,pipeline", [(10, 0, 0), (0, 0, 0), (10, 0, 1), (0, 0, 1), (10, 1, 0)])
+def test_short_horizon_against_oracle(kind, steps, mode, sort_every, g2p_mode, pipeline):
     """100 substeps of a two-ball impact: per-particle position / velocity error, mass, momentum.
-    sort_every=0 never re-bins after the upload: the thrown ball drifts ~1 cell, so the staged
-    kernels see particles in neighbouring window rows and beyond (their global-memory path).
-    fuse_mode 0 = separate kernels (default), 1 = the fused G2P2G pipeline."""
+    sort_every=0 never re-bins after the upload: the thrown ball drifts ~1 cell, so the kernels work
+    on a stale order.  pipeline 0 = hand-over (default: G2P leaves the next P2G's affine matrix in the C
+    rows between the substeps of one mpm_advance call), 1 = classic (every P2G evaluates the material);
+    the hand-over run advances in calls of 1, 7 and the rest, so both forms of the particle state meet
+    every kind of substep."""
     N = 32
     p, mats = scenes.two_spheres(N, kind=kind, perturb=False)
-    sim = _sim(N, mats, kind, mode, sort_every=sort_every, g2p_mode=g2p_mode, fuse_mode=fuse_mode)
+    sim = _sim(N, mats, kind, mode, sort_every=sort_every, g2p_mode=g2p_mode, pipeline=pipeline)
     sim.upload(p)
-    sim.advance(steps)
+    sim.advance(1)
+    sim.advance(7)
+    sim.advance(steps - 8)
     got = sim.download()
     ref, _ = ol.advance(p.copy(), mats, DT, N, kind, steps)
     dx = 1.0 / N
@@ -200,11 +204,12 @@ def test_g2p_tile_handles_stale_order_and_domain_faces():
 
 @pytest.mark.parametrize("kind", [ol.SNOW, ol.FIXED_COROTATED])
 @pytest.mark.parametrize("sort_every", [0, 3])
-def test_fused_pipeline_matches_separate_kernels(kind, sort_every):
-    """G2P2G (one kernel, two alternating grids) against reset -> P2G -> grid update -> G2P as
-    separate kernels: particles over the whole domain (clipped stencils, out-of-domain particles
-    that both paths must leave untouched), fast enough to change cells between re-bins, several
-    materials, and the look-ahead grid invalidated in mid-run by an overwrite and by single-stage
+def test_handover_pipeline_matches_classic(kind, sort_every):
+    """Hand-over (G2P computes the next P2G's affine matrix) against the classic pipeline (every P2G
+    evaluates the material itself): particles over the whole domain (clipped stencils, out-of-domain
+    particles that both paths must leave untouched, particles that LEAVE the domain in mid-call and
+    must keep the reference's C), fast enough to change cells between re-bins, several materials,
+    fixed-corotated particles with Jp != 1, and particle data replaced / single stages run between the
     calls.  Same arithmetic per particle, so the only difference is the order of the atomic sums."""
     N = 32
     rng = np.random.default_rng(23)
@@ -212,43 +217,50 @@ def test_fused_pipeline_matches_separate_kernels(kind, sort_every):
     nb = int((p["x"][:, 1] > 0.45).sum())
     p["v"][p["x"][:, 1] > 0.45] = [5.0, -30.0, 2.0]   # the thrown ball crosses a cell in ~10 substeps
     p["C"] *= 0.2
-    # a resting sheet that pokes through the x = 0 face (clipped stencils, sticky-wall nodes) and a
-    # few particles far outside the domain, which both pipelines must leave untouched
+    # a resting sheet that pokes through the x = 0 face (clipped stencils, sticky-wall nodes), a few
+    # particles far outside the domain, which both pipelines must leave untouched, and a few just inside
+    # the z = 1 face flying out: they leave the domain during the first call
     sheet = ol.new_particles(rng.uniform([-0.045, 0.3, 0.3], [0.08, 0.5, 0.5], (4000, 3)).astype(np.float32))
+    leaving = ol.new_particles(rng.uniform([0.3, 0.3, 1.0 - 0.3 / N], [0.5, 0.5, 1.0 - 0.1 / N], (200, 3)).astype(np.float32))
+    leaving["v"][:, 2] = 60.0   # 0.3 cells in 1.6 substeps: out of the domain (base node >= N) within the first call
     far = ol.new_particles(rng.uniform(1.05, 1.2, (64, 3)).astype(np.float32))
     far["v"] = 1.0
-    p = np.concatenate([p, sheet, far])
+    p = np.concatenate([p, sheet, leaving, far])
     n = len(p)
     p["material_type"] = rng.integers(0, 2, n).astype(np.uint8)
     vol = 1.0 / 500000.0
     if kind == ol.SNOW:
         mats = np.stack([ol.make_material(vol), ol.make_material(vol, 400.0, 1.0e5, 0.3, 5.0, 0.97, 1.01)])
     else:
-        p["Jp"] = 1.0
+        p["Jp"] = (1.0 + 0.05 * rng.standard_normal(n)).astype(np.float32)  # the fixed-corotated lambda term
         mats = np.stack([ol.make_material(vol, 1000.0, 1.4e5, 0.2, 0.0, 0.0, 1e30),
                          ol.make_material(vol, 500.0, 0.7e5, 0.3, 0.0, 0.0, 1e30)])
     outs = []
-    for fuse_mode in (1, 0):
-        sim = _sim(N, mats, kind, 0, sort_every=sort_every, fuse_mode=fuse_mode)
+    for pipeline in (0, 1):
+        sim = _sim(N, mats, kind, 0, sort_every=sort_every, pipeline=pipeline)
         sim.upload(p)
+        if kind != ol.SNOW:
+            assert sim.diagnostics()["jp_not_one"] == 1
         sim.advance(4)
         mid = sim.download()
         mid["v"][:-64, 1] += np.float32(0.25)
-        sim.overwrite(mid)        # particles changed behind the pipeline's back
+        sim.overwrite(mid)        # particles changed between two calls
         sim.advance(3)
-        sim.stage("reset_grid")   # single stages in between: the look-ahead grid is rebuilt afterwards
+        sim.stage("reset_grid")   # single stages in between
         sim.stage("p2g")
         sim.advance(3)
         outs.append(sim.download())
         sim.close()
     a, b = outs
     assert a[-64:].tobytes() == p[-64:].tobytes() and b[-64:].tobytes() == p[-64:].tobytes()
-    assert nb > 1000 and np.isfinite(a["x"]).all() and np.abs(a["x"][:-64]).max() < 1.0
+    assert nb > 1000 and np.isfinite(a["x"]).all() and np.abs(a["x"][:-264]).max() < 1.0
+    gone = a["x"][-264:-64, 2] > 1.0 + 1.0 / N
+    assert gone.sum() > 20, "some of the leaving particles must have left the domain"
     errs = {f: float(np.abs(a[f].astype(np.float64) - b[f]).max() / max(np.abs(b[f]).max(), 1e-6)) for f in ("x", "v", "F", "C", "Jp")}
-    print("fused vs separate, max error / field maximum:", {f: f"{e:.1e}" for f, e in errs.items()})
+    print("hand-over vs classic, max error / field maximum:", {f: f"{e:.1e}" for f, e in errs.items()})
     # Two runs of EITHER pipeline differ by the order of the atomic sums (~1e-7 per substep), which the
     # stiff two-ball contact amplifies over the 10 substeps; measured 1e-6 .. 2e-5 depending on the run.
-    # A synchronisation bug would show as O(1e-2 .. 1).
+    # A particle left with the affine matrix in place of C would show as O(1).
     for f, e in errs.items():
         assert e <= 2e-4, (f, errs)
     # against the oracle on the same schedule
@@ -257,6 +269,8 @@ def test_fused_pipeline_matches_separate_kernels(kind, sort_every):
     ref, _ = ol.advance(ref, mats, DT, N, kind, 6)
     assert np.abs(a["x"].astype(np.float64) - ref["x"]).max() * N < 1e-3
     assert np.abs(a["v"].astype(np.float64) - ref["v"]).max() <= 1e-3 * np.abs(ref["v"]).max()
+    c_scale = np.abs(ref["C"]).max()
+    assert np.abs(a["C"].astype(np.float64) - ref["C"]).max() <= 2e-3 * c_scale
 
 
 def test_adaptive_rebin_on_measured_disorder():
@@ -319,23 +333,23 @@ def test_full_size_properties_config4():
     sortedness of the cell keys, exact particle count, grid mass = P * m after P2G, no NaN."""
     N, P = 256, 1 << 26
     mats = ol.make_material(0.512 / P, 1000.0, 1.4e5, 0.2, 0.0, 0.0, 1e30)
-    sim = _sim(N, mats, ol.FIXED_COROTATED, mode=1, sort_every=8, fuse_mode=1)
+    sim = _sim(N, mats, ol.FIXED_COROTATED, mode=1, sort_every=8)
     sim.generate_dense_block(P, seed=1234)
     assert sim.count == P
     keys, ids = sim.sort_state()
     assert (np.diff(keys.astype(np.int64)) >= 0).all()
     assert np.array_equal(np.sort(ids), np.arange(P, dtype=np.uint32))  # a permutation
     del keys, ids
-    sim.advance(3)   # fused pipeline: the grid now holds the look-ahead of substep 4 ...
+    sim.advance(3)   # the grid holds the velocities of substep 3
     g = sim.grid()
     assert np.isfinite(g).all()
-    assert (g[..., 3] > 0).sum() > 0.5 * 205 ** 3  # ... scattered from every occupied cell
+    assert (g[..., 3] > 0).sum() > 0.5 * 205 ** 3  # scattered from every occupied cell
     sim.stage("reset_grid")
     sim.stage("p2g")
     g = sim.grid()
     mass = float(mats[1])
     assert abs(g[..., 3].sum(dtype=np.float64) - mass * P) <= 1e-5 * mass * P
     assert np.isfinite(g).all()
-    sim.advance(2)   # look-ahead rebuilt after the single-stage calls
+    sim.advance(2)
     x = sim.download_positions()
     assert np.isfinite(x).all() and x.min() > 0.09 and x.max() < 0.91

@@ -60,7 +60,7 @@ def test_svd3_live_reference_bit_exact():
         assert (x.view(np.uint32) == y.view(np.uint32)).all()
 
 
-@pytest.mark.parametrize("name,kind", [("snow", ol.SNOW), ("fc", ol.FIXED_COROTATED)])
+@pytest.mark.parametrize("name,kind", [("snow", ol.SNOW), ("fc", ol.FIXED_COROTATED), ("jelly", ol.JELLY)])
 def test_substep_golden_bit_exact(name, kind):
     """Oracle == the reference's own plugin headers + kernel bodies (host build), bit for bit,
     stage by stage and over a 21-step horizon."""
@@ -79,7 +79,7 @@ def test_substep_golden_bit_exact(name, kind):
     ol.set_threads(ol.max_threads())
 
 
-@pytest.mark.parametrize("kind", [ol.SNOW, ol.FIXED_COROTATED])
+@pytest.mark.parametrize("kind", [ol.SNOW, ol.FIXED_COROTATED, ol.JELLY])
 def test_substep_live_reference(kind):
     ref = ol.Ref(kind)
     if not ref.available:

@@ -24,6 +24,6 @@ else:
         try:
             d = json.loads(r.stdout.strip().splitlines()[-1])
             st = d["stage_ms"]
-            print(f"{name:24s} step {d['ms_per_step']:.3f} ms | p2g {st['p2g']:.3f} g2p {st['g2p']:.3f} g2p2g {st.get('g2p2g', 0):.3f} sort {st['sort']:.3f} grid {st['grid']:.3f} reset {st['reset']:.3f} | frac {d['substep_roofline']['frac']:.3f}", flush=True)
+            print(f"{name:24s} step {d['ms_per_step']:.3f} ms | p2g {st['p2g']:.3f} g2p {st['g2p']:.3f} sort {st['sort']:.3f} grid {st['grid']:.3f} reset {st['reset']:.3f} | frac {d['substep_roofline']['frac']:.3f}", flush=True)
         except Exception as e:
             print(name, "FAILED", e, r.stderr[-800:], flush=True)
