@@ -7,9 +7,15 @@ N=1 workload = BASELINE.json configs[3]: synthetic dense block, N=256, 2^26 part
 fixed-corotated.  For N>1 (launched with torch.distributed.run, one
 rank per GPU) every rank keeps 2^26 particles and ~2^24 grid nodes (weak scaling): the cubic
 domain grows to N = 256 * gpus^(1/3) and is cut into x-slabs balanced by particle count.
-A "step" is one substep (grid reset -> P2G -> [halo exchange] -> grid update -> G2P), the sort is
+A "step" is one substep (grid reset -> P2G -> [halo exchange] -> grid update -> G2P), the re-bin is
 included at its cadence (--sort-every).  Inputs are generated on the device and are far larger
 than L2 (6.7 GB particles + 268 MB grid per GPU), so no L2 flush is needed between steps.
+
+Outside the timed region the run checks itself (exit code 3 on failure): particle count, grid mass
+after P2G, finiteness ("invariants"), and at N > 1 a small scene on the same N slabs against the CPU
+checker ("parity_nranks").  Further keys of the JSON line: the other BASELINE.json configurations
+("configs": snow = configs[4], strong scaling of configs[3]) and stressed variants of the workload
+("stressed": shear flow + perturbed F, snow that yields, bit-exact svd3 mode).
 """
 import argparse
 import json
@@ -31,8 +37,8 @@ BYTES_PER_NODE = 80        # zero 16 + P2G write-back 16 + grid update 16+16 + G
 # per-kernel algorithmic bytes (DESIGN.md "Kernels"): (bytes per particle, bytes per node)
 KERNEL_BYTES = {"reset": (0, 16), "p2g": (100, 16), "grid": (0, 32), "g2p": (152, 16)}
 # what the kernels of the hand-over pipeline actually have to move: P2G reads v, A, x
-# (60 B), G2P reads x, F (, Jp) and writes 24 (25) streams; reported beside the SURVEY formula
-MOVED_BYTES = {"reset": (0, 16), "p2g": (60, 16), "grid": (0, 32), "g2p": (144, 16)}
+# (60 B); G2P reads x, F (, Jp) and writes every stream it owns.  Reported beside the SURVEY formula.
+MOVED_BYTES = {"fixed_corotated": {"p2g": 60, "g2p": 48 + 96}, "snow": {"p2g": 60, "g2p": 52 + 100}}
 E2E_SUBSTEPS_PER_SYNC = 20  # the reference main loop calls syncDevice every 20 advances (src/main.cu:99)
 
 
@@ -45,7 +51,7 @@ def peaks():
 
 def ncu_traffic(kernel, particles, nodes):
     """dram bytes read + written per launch of `kernel` from the committed ncu --set full capture of
-    this workload (profiles/ncu_traffic.json, written by tools/ncu_summary.py); None if the capture
+    this workload (profiles/ncu_traffic.json, written from the capture named there); None if the capture
     was taken at another size."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     try:
@@ -125,20 +131,38 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
-def run_reference(args):
-    """The reference has no CPU substep; this arm times the declared OpenMP transcription of its
-    mpm.cu loops (oracle/, bit-exact against the reference's own headers) on the host cores, on a
-    bounded sample of the same workload: the dense block at the same particles-per-cell."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+# --------------------------------------------------------------------------------------------------
+# CPU arms (the only places that execute the checker under oracle/)
+# --------------------------------------------------------------------------------------------------
+def _cpu_threads():
+    """All host cores: torch.distributed.run exports OMP_NUM_THREADS=1, which is not the machine."""
+    import oracle_lib as ol
+
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    ol.set_threads(n)
+    return n
+
+
+def _cpu_sample():
     import oracle_lib as ol
     import scenes
 
     N, P = 64, 1 << 20  # same generator, same 7.8 particles per cell as N=256 / 2^26
     p, mats = scenes.dense_block(P, N, density=P / 0.512)
-    grid = ol.new_grid(N)
-    threads = ol.max_threads()
+    return N, P, p, mats, ol.new_grid(N)
+
+
+def run_reference(args):
+    """The reference has no CPU substep; this arm times the declared OpenMP transcription of its
+    mpm.cu loops (oracle/, bit-exact against the reference's own headers) on all host cores, on a
+    bounded sample of the same workload: the dense block at the same particles-per-cell."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle_lib as ol
+
+    threads = _cpu_threads()
+    N, P, p, mats, grid = _cpu_sample()
     for _ in range(args.warmup):
         ol.advance(p, mats, 1e-4, N, ol.FIXED_COROTATED, 1, grid)
     t0 = time.perf_counter()
@@ -146,7 +170,7 @@ def run_reference(args):
         ol.advance(p, mats, 1e-4, N, ol.FIXED_COROTATED, 1, grid)
     dt = time.perf_counter() - t0
     value = P * args.steps / dt
-    sample = f"dense block N={N}, {P} particles (7.8 ppc as in the full workload), fixed-corotated, {args.steps} substeps"
+    sample = f"dense block N={N}, {P} particles (7.8 ppc as in the full workload), fixed-corotated, {args.steps} substeps, OpenMP {threads} threads"
     print(json.dumps({
         "impl": "reference", "metric": "particle_steps_per_s", "value": value, "unit": "particle-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
@@ -160,12 +184,9 @@ def run_reference(args):
 
 def cpu_baseline(seconds_budget=20.0):
     import oracle_lib as ol
-    import scenes
 
-    N, P = 64, 1 << 20
-    p, mats = scenes.dense_block(P, N, density=P / 0.512)
-    grid = ol.new_grid(N)
-    threads = ol.max_threads()
+    threads = _cpu_threads()
+    N, P, p, mats, grid = _cpu_sample()
     ol.advance(p, mats, 1e-4, N, ol.FIXED_COROTATED, 1, grid)
     steps, t0 = 0, time.perf_counter()
     while steps < 3 or (time.perf_counter() - t0 < seconds_budget / 2 and steps < 50):
@@ -174,6 +195,200 @@ def cpu_baseline(seconds_budget=20.0):
     dt = time.perf_counter() - t0
     return {"value": P * steps / dt, "unit": "particle-steps/s", "cores": threads, "kind": "port",
             "sample": f"dense block N={N}, {P} particles (7.8 ppc), fixed-corotated, {steps} substeps, OpenMP {threads} threads"}
+
+
+# --------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------
+class Ctx:
+    """Rank layout + helpers shared by the legs of one run."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist, self.args = torch, dist, args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world != args.gpus:
+            if self.rank == 0:
+                print(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={self.world}; launch with torch.distributed.run", file=sys.stderr)
+            sys.exit(2)
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; the substep has no CPU fallback")
+        torch.cuda.set_device(self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def reduce(self, values, op="sum"):
+        t = self.torch.tensor(values, dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM if op == "sum" else self.dist.ReduceOp.MAX)
+        return [float(v) for v in t]
+
+    def fail(self, what):
+        print(f"bench.py: self-check failed on rank {self.rank}: {what}", file=sys.stderr, flush=True)
+        sys.exit(3)
+
+
+def make_sim(ctx, model, scaling, particles_per_gpu, svd, sort_every, pipeline="handover", p2g="runs", g2p="tile", rebin_permille=0, ghost=0):
+    import mpm_b200
+
+    N, slabs = workload(ctx.world, scaling)
+    xb, xe = slabs[ctx.rank]
+    P_total = particles_per_gpu * (ctx.world if scaling == "weak" else 1)
+    density = P_total / 0.512  # --particle-count: the block fills 0.8^3 of the unit cube
+    snow = model == "snow"
+    if snow:  # scenes/snowman.toml material
+        mats = mpm_b200.make_material(1.0 / density, 700.0, 1.4e5, 0.2, 10.0, 0.975, 1.0075)
+    else:
+        mats = mpm_b200.make_material(1.0 / density, 1000.0, 1.4e5, 0.2, 0.0, 0.0, 1e30)
+    cap = int(P_total / ctx.world * 1.15) if ctx.world > 1 else 0
+    sim = mpm_b200.Sim(N, 1e-4, mats, model=mpm_b200.SNOW if snow else mpm_b200.FIXED_COROTATED,
+                       svd_mode=mpm_b200.SVD_FAST if svd == "fast" else mpm_b200.SVD_EXACT, sort_every=sort_every,
+                       x_begin=xb, x_end=xe, device=ctx.local_rank, capacity=cap,
+                       p2g_mode=mpm_b200.P2G_RUNS if p2g == "runs" else mpm_b200.P2G_DIRECT,
+                       g2p_mode=mpm_b200.G2P_TILE if g2p == "tile" else mpm_b200.G2P_DIRECT,
+                       pipeline=mpm_b200.PIPE_HANDOVER if pipeline == "handover" else mpm_b200.PIPE_CLASSIC,
+                       rebin_permille=rebin_permille, ghost=ghost)
+    if ctx.world > 1:
+        from mpm_b200 import slabs as _slabs
+
+        sim.attach_comm(_slabs.share_unique_id(ctx.dist, ctx.rank, mpm_b200.comm_unique_id), ctx.rank, ctx.world)
+    return sim, N, slabs, P_total, float(mats[1])
+
+
+def timed(ctx, sim, steps, warmup):
+    """W untimed substeps, then K substeps between CUDA events on the handle's stream, barrier +
+    synchronize on both sides; returns (ms max over ranks, launches, host monotonic window)."""
+    torch = ctx.torch
+    stream = torch.cuda.ExternalStream(sim.stream)
+    left = warmup
+    while left > 0:  # in calls of several substeps, so that the hand-over pipeline is warm too
+        sim.advance(min(left, 4))
+        left -= 4
+    sim.sync()
+    ctx.barrier()
+    t0 = time.monotonic()
+    launches0 = sim.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    sim.advance(steps)
+    e1.record(stream)
+    sim.sync()
+    ctx.barrier()
+    ms = ctx.reduce([e0.elapsed_time(e1)], "max")[0]
+    return ms, sim.launches - launches0, (t0, time.monotonic())
+
+
+def short_leg(ctx, model, scaling, svd, steps, shear=0.0, f_noise=0.0, particles=P_PER_GPU, sort_every=8):
+    """One more workload, measured like the main one but shorter; returns a small dict."""
+    ghost = 0
+    if shear and ctx.world > 1:
+        # slab handles: the fastest particles (0.4 shear m/s at the block faces) must stay within the ghost
+        # planes between two re-bins, or the re-bin fails (MpmDiagnostics.escaped): 2 ghost planes, cadence 4
+        ghost, sort_every = 2, 4
+    sim, N, slabs, P_total, _ = make_sim(ctx, model, scaling, particles, svd, sort_every, ghost=ghost)
+    sim.generate_dense_block(P_total, seed=1234, shear=shear, f_noise=f_noise)
+    sim.sync()
+    ms, _, _ = timed(ctx, sim, steps, 8)
+    P_all = ctx.reduce([float(sim.count)])[0]
+    diag = sim.diagnostics()
+    sim.close()
+    if abs(P_all - P_total) > 0.5:
+        ctx.fail(f"{model}/{scaling}: {P_all} particles on the ranks, {P_total} generated")
+    return {"N": N, "particles": int(P_all), "model": model, "svd_mode": svd, "scaling": scaling if ctx.world > 1 else "n/a",
+            "ms_per_step": ms / steps, "value": P_all / (ms / steps * 1e-3), "unit": "particle-steps/s", "steps": steps,
+            "shear": shear, "f_noise": f_noise, "sort_every": sort_every, "ghost": ghost, "nonfinite": diag["nonfinite"]}
+
+
+def parity_nranks(ctx):
+    """A small sheared block on the SAME number of slabs, every rank holding and exchanging particles
+    in both directions, against the CPU checker on rank 0 (per-particle position / velocity error)."""
+    import mpm_b200
+    import oracle_lib as ol
+    import scenes
+    from mpm_b200 import slabs as sl
+
+    W = ctx.world
+    N = max(32, 8 * W)  # slabs of >= 8 planes
+    P, steps, dt = 200_000, 40, 1e-4
+    # v_x = shear * (y - 0.5): +x above the mid-plane, -x below, so particles cross every slab boundary both ways
+    p, mats = scenes.dense_block(P, N, kind=ol.SNOW, shear=40.0, f_noise=0.01)
+    slabs = sl.balanced_slabs(N, W, 0.1, 0.9)
+    own = sl.owner(p["x"][:, 0], N, slabs)
+    xb, xe = slabs[ctx.rank]
+    sim = mpm_b200.Sim(N, dt, mats, model=mpm_b200.SNOW, svd_mode=mpm_b200.SVD_EXACT, sort_every=4, x_begin=xb, x_end=xe,
+                       device=ctx.local_rank, capacity=P)
+    sim.attach_comm(sl.share_unique_id(ctx.dist, ctx.rank, mpm_b200.comm_unique_id), ctx.rank, W)
+    mine = np.where(own == ctx.rank)[0]
+    sim.upload_with_ids(np.ascontiguousarray(p[mine]), mine.astype(np.uint32))
+    sim.advance(steps)
+    got = sim.download()
+    _, ids = sim.sort_state()
+    diag = sim.diagnostics()
+    sim.close()
+    box = [None] * W if ctx.rank == 0 else None
+    ctx.dist.gather_object((ids, got, len(mine), diag), box, dst=0)
+    out = None
+    if ctx.rank == 0:
+        _cpu_threads()
+        ref, _ = ol.advance(p.copy(), mats, dt, N, ol.SNOW, steps)
+        merged = np.zeros_like(p)
+        seen = np.zeros(P, np.int32)
+        moved_up = moved_down = 0
+        for r, (ids_r, got_r, n0, _) in enumerate(box):
+            merged[ids_r] = got_r
+            seen[ids_r] += 1
+            moved_up += int((own[ids_r] < r).sum())
+            moved_down += int((own[ids_r] > r).sum())
+        ok_once = bool((seen == 1).all())
+        err_x = float(np.abs(merged["x"].astype(np.float64) - ref["x"]).max() * N) if ok_once else float("inf")
+        err_v = float(np.abs(merged["v"].astype(np.float64) - ref["v"]).max()) if ok_once else float("inf")
+        vmax = float(np.abs(ref["v"]).max())
+        out = {"ranks": W, "N": N, "particles": P, "substeps": steps, "model": "snow", "svd_mode": "exact",
+               "max_dx_over_dx": err_x, "max_dv": err_v, "v_max": vmax, "migrated_up": moved_up, "migrated_down": moved_down,
+               "escaped": int(sum(b[3]["escaped"] for b in box)), "every_particle_on_one_rank": ok_once,
+               "tolerance": {"dx_over_dx": 1e-3, "dv_over_vmax": 1e-3},
+               "ok": ok_once and err_x < 1e-3 and err_v < 1e-3 * vmax and moved_up > 0 and moved_down > 0}
+    flag = ctx.reduce([0.0 if (out is None or out["ok"]) else 1.0])[0]
+    if flag:
+        ctx.fail(f"parity on {W} slabs: {out}")
+    return out
+
+
+def invariants(ctx, sim, P_total, mass, slab, N):
+    """Size-independent self-checks on the benchmark state (outside every timed region)."""
+    P_all = ctx.reduce([float(sim.count)])[0]
+    if abs(P_all - P_total) > 0.5:
+        ctx.fail(f"{P_all} particles on the ranks, {P_total} generated")
+    sim.stage("reset_grid")
+    sim.stage("p2g")  # on slab handles including the halo exchange
+    g = sim.grid()
+    x0 = max(0, slab[0] - 1) if ctx.world > 1 else 0  # first local plane (ghost = 1)
+    own = g[slab[0] - x0: slab[1] - x0]
+    finite = bool(np.isfinite(g).all())
+    m_all = ctx.reduce([float(own[..., 3].sum(dtype=np.float64))])[0]
+    del g, own
+    x = sim.download_positions()
+    finite = finite and bool(np.isfinite(x).all())
+    inside = bool(((x > 0.0) & (x < 1.0)).all())
+    del x
+    diag = sim.diagnostics()
+    bad = ctx.reduce([0.0 if finite and inside else 1.0, float(diag["escaped"]), float(diag["nonfinite"])])
+    rel = abs(m_all - P_total * mass) / (P_total * mass)
+    out = {"particles": int(P_all), "particles_expected": int(P_total), "grid_mass_rel_err": rel, "grid_mass_tolerance": 1e-5,
+           "finite_and_inside_domain": bad[0] == 0.0, "escaped": int(bad[1]), "nonfinite": int(bad[2]),
+           "ok": bad[0] == 0.0 and bad[1] == 0.0 and bad[2] == 0.0 and rel < 1e-5}
+    if not out["ok"]:
+        ctx.fail(f"invariants: {out}")
+    return out
 
 
 def main():
@@ -198,89 +413,30 @@ def main():
                     help="material model; snow = BASELINE.json configs[4] (plasticity via svd3 in G2P)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra configurations / stressed workloads / N-rank parity")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
 
-    import torch
-    import torch.distributed as dist
+    ctx = Ctx(args)
+    torch, rank, world = ctx.torch, ctx.rank, ctx.world
+    full = args.particles == P_PER_GPU and not args.no_extras
 
-    import mpm_b200
+    parity = parity_nranks(ctx) if (world > 1 and not args.no_extras) else None
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if rank == 0:
-            print(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; launch with torch.distributed.run", file=sys.stderr)
-        sys.exit(2)
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the substep has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    N, slabs = workload(world, args.scaling)
-    xb, xe = slabs[rank]
-    P_total = args.particles * (world if args.scaling == "weak" else 1)
-    dt = 1e-4
-    density = P_total / 0.512  # --particle-count: the block fills 0.8^3 of the unit cube
-    snow = args.model == "snow"
-    if snow:  # scenes/snowman.toml material
-        mats = mpm_b200.make_material(1.0 / density, 700.0, 1.4e5, 0.2, 10.0, 0.975, 1.0075)
-    else:
-        mats = mpm_b200.make_material(1.0 / density, 1000.0, 1.4e5, 0.2, 0.0, 0.0, 1e30)
-    svd_mode = mpm_b200.SVD_FAST if args.svd == "fast" else mpm_b200.SVD_EXACT
-    cap = int(P_total / world * 1.15) if world > 1 else 0
-    sim = mpm_b200.Sim(N, dt, mats, model=mpm_b200.SNOW if snow else mpm_b200.FIXED_COROTATED, svd_mode=svd_mode, sort_every=args.sort_every,
-                       x_begin=xb, x_end=xe, device=local_rank, capacity=cap,
-                       p2g_mode=mpm_b200.P2G_RUNS if args.p2g == "runs" else mpm_b200.P2G_DIRECT,
-                       g2p_mode=mpm_b200.G2P_TILE if args.g2p == "tile" else mpm_b200.G2P_DIRECT,
-                       pipeline=mpm_b200.PIPE_HANDOVER if args.pipeline == "handover" else mpm_b200.PIPE_CLASSIC,
-                       rebin_permille=args.rebin_permille)
-    if world > 1:
-        from mpm_b200 import slabs as _slabs
-
-        sim.attach_comm(_slabs.share_unique_id(dist, rank, mpm_b200.comm_unique_id), rank, world)
+    sim, N, slabs, P_total, mass = make_sim(ctx, args.model, args.scaling, args.particles, args.svd, args.sort_every, args.pipeline,
+                                            args.p2g, args.g2p, args.rebin_permille)
     sim.generate_dense_block(P_total, seed=1234, shear=args.shear, f_noise=args.f_noise)
     sim.sync()
-    P_local = sim.count
-    G_local = sim.grid_nodes
+    P_local, G_local = sim.count, sim.grid_nodes
+    inv = invariants(ctx, sim, P_total, mass, slabs[rank], N)
 
-    stream = torch.cuda.ExternalStream(sim.stream)
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(ctx.local_rank)
     if rank == 0:
         sampler.start()
-    for _ in range(args.warmup):
-        sim.advance(1)
-    sim.sync()
-    barrier()
-    t_region0 = time.monotonic()
-    launches0 = sim.launches
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    sim.advance(args.steps)
-    e1.record(stream)
-    sim.sync()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    launches = sim.launches - launches0
-    clocks = sampler.stop(t_region0, time.monotonic()) if rank == 0 else None
-    t = torch.tensor([ms, float(P_local), float(G_local)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        tmax = t.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone()
-        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        ms = float(tmax[0])
-        P_all, G_all = float(tsum[1]), float(tsum[2])
-    else:
-        P_all, G_all = float(P_local), float(G_local)
+    ms, launches, window = timed(ctx, sim, args.steps, args.warmup)
+    clocks = sampler.stop(*window) if rank == 0 else None
+    P_all, G_all = ctx.reduce([float(P_local), float(G_local)])
     ms_per_step = ms / args.steps
     value = P_all / (ms_per_step * 1e-3)
 
@@ -291,7 +447,7 @@ def main():
     sim.advance(n_prof)
     st = sim.stage_times()
     sim.set_stage_timing(False)
-    barrier()
+    ctx.barrier()
     peak, peak_src = peaks()
     substep_keys = ("reset", "p2g", "grid", "g2p")
     dom = max(substep_keys, key=lambda s: st[s])
@@ -301,9 +457,21 @@ def main():
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic(dom, P_local, G_local), "peak_source": peak_src, "kernel_ms": dom_ms,
                 "algorithmic_bytes_per_launch": bp * P_local + bn * G_local}
+    per_kernel = {}
+    for s in substep_keys:
+        kp, kn = KERNEL_BYTES[s]
+        t_ms = st[s] / n_prof
+        if t_ms <= 0:
+            continue
+        rec = {"ms": t_ms, "frac": (kp * P_local + kn * G_local) / (t_ms * 1e-3) / 1e9 / peak}
+        if args.pipeline == "handover" and s in MOVED_BYTES[args.model]:
+            rec["frac_on_bytes_moved"] = (MOVED_BYTES[args.model][s] * P_local + kn * G_local) / (t_ms * 1e-3) / 1e9 / peak
+        per_kernel[s] = rec
     sub_ach = (BYTES_PER_PARTICLE * P_all + BYTES_PER_NODE * G_all) / (ms_per_step * 1e-3) / 1e9 / world
     substep_roofline = {"achieved_per_gpu": sub_ach, "peak": peak, "unit": "GB/s", "frac": sub_ach / peak,
-                        "bytes": "252*P + 80*G per substep (BASELINE.md)"}
+                        "bytes": "252*P + 80*G per substep (SURVEY.md 8(d))", "per_kernel": per_kernel,
+                        "note": "frac = SURVEY 8(d) algorithmic bytes / time / measured copy peak; with the hand-over pipeline the kernels "
+                                "move fewer bytes than that (P2G 60 B/particle instead of 100): per_kernel.frac_on_bytes_moved"}
     stage_ms = {k: v / n_prof for k, v in st.items()}
 
     # e2e: host AoS buffers through the C ABI, the reference's own cadence: upload (initCuda),
@@ -314,26 +482,44 @@ def main():
         host = torch.empty(n_host * 104, dtype=torch.uint8, pin_memory=True)
         got = sim.download_ptr(host.data_ptr(), n_host)  # current state as the host-side truth
         assert got == n_host
-        barrier()
+        ctx.barrier()
         frames = 2
         t0 = time.perf_counter()
         for _ in range(frames):
             sim.upload_ptr(host.data_ptr(), n_host)
             sim.advance(E2E_SUBSTEPS_PER_SYNC)
             sim.download_ptr(host.data_ptr(), n_host)
-        barrier()
-        wall = time.perf_counter() - t0
-        tw = torch.tensor([wall], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(tw, op=dist.ReduceOp.MAX)
-        wall = float(tw[0])
+        ctx.barrier()
+        wall = ctx.reduce([time.perf_counter() - t0], "max")[0]
         e2e = {"value": P_all * E2E_SUBSTEPS_PER_SYNC * frames / wall, "unit": "particle-steps/s",
                "h2d_bytes_per_step": n_host * 104 / E2E_SUBSTEPS_PER_SYNC, "d2h_bytes_per_step": n_host * 104 / E2E_SUBSTEPS_PER_SYNC,
                "substeps_per_sync": E2E_SUBSTEPS_PER_SYNC,
                "what": "mpm_upload_particles_aos (pinned host AoS, 104 B/particle) + 20 x mpm_advance + mpm_download_particles_aos per frame; bytes are per substep"}
         del host
+    sim.close()
+
+    # the other BASELINE.json configurations and stressed variants of the workload, each its own short
+    # run (2^26 particles per GPU, N as the main run): driver-visible numbers for configs[3] strong
+    # scaling and configs[4] (snow), and for inputs that are not at rest (the quiescent block
+    # is the cheapest case of every data-dependent path)
+    configs, stressed = None, None
+    if full:
+        k = max(8, min(args.steps, 16))
+        configs = {"config5_snow": short_leg(ctx, "snow", args.scaling, "fast", k)}
+        if world > 1:
+            configs["config4_fixed_corotated_strong"] = short_leg(ctx, "fixed_corotated", "strong", "fast", k)
+        stressed = {
+            "what": "same block, v = shear * (y - 0.5, 0, 0.3 (x - 0.5)) (0.2 cells per substep at the faces for shear 20 at N = 256) and "
+                    "F = I + f_noise * u[-1,1): Newton polar iterates, snow yields (|F - I| up to 5 % against an elastic range of "
+                    "-2.5 % / +0.75 %), particles cross cells between re-bins",
+            "fixed_corotated_sheared": short_leg(ctx, "fixed_corotated", args.scaling, "fast", k, shear=20.0, f_noise=0.05),
+            "snow_yielding": short_leg(ctx, "snow", args.scaling, "fast", k, shear=20.0, f_noise=0.05),
+        }
+        if world == 1:
+            stressed["snow_exact_svd"] = short_leg(ctx, "snow", args.scaling, "exact", 8)
 
     if rank == 0:
+        snow = args.model == "snow"
         out = {
             "metric": "particle_steps_per_s", "value": value, "unit": "particle-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -341,18 +527,24 @@ def main():
             "config": {"workload": f"synthetic dense block N={N}, {int(P_all)} particles, {args.model} (BASELINE.json configs[{4 if snow else 3}]"
                                    + (")" if world == 1 else (f" scaled weakly to {world} GPUs: 2^26 particles and ~2^24 nodes per GPU)" if args.scaling == "weak"
                                                               else f" strong scaling: the same block cut into {world} slabs)")),
-                       "N": N, "particles": int(P_all), "grid_nodes": int(G_all), "dt": dt, "model": args.model,
-                       "svd_mode": args.svd, "sort_every": args.sort_every, "rebin_permille": args.rebin_permille, "p2g": args.p2g, "g2p": args.g2p, "pipeline": args.pipeline, "shear": args.shear, "f_noise": args.f_noise, "slabs": slabs if world > 1 else None,
+                       "N": N, "particles": int(P_all), "grid_nodes": int(G_all), "dt": 1e-4, "model": args.model,
+                       "svd_mode": args.svd, "sort_every": args.sort_every, "rebin_permille": args.rebin_permille, "p2g": args.p2g, "g2p": args.g2p,
+                       "pipeline": args.pipeline, "shear": args.shear, "f_noise": args.f_noise, "slabs": slabs if world > 1 else None,
                        "l2": "inputs (6.7 GB particles + 268 MB grid per GPU) are far larger than the 126 MB L2; no flush"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "substep_roofline": substep_roofline, "stage_ms": stage_ms,
+            "substep_roofline": substep_roofline, "stage_ms": stage_ms, "invariants": inv,
         }
+        if parity is not None:
+            out["parity_nranks"] = parity
+        if configs is not None:
+            out["configs"] = configs
+        if stressed is not None:
+            out["stressed"] = stressed
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline()
         print(json.dumps(out))
-    sim.close()
     if world > 1:
-        dist.destroy_process_group()
+        ctx.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

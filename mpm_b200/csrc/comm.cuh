@@ -90,7 +90,7 @@ struct Comm {
   size_t mig_cap = 0;
   float* send_buf = nullptr;  // 2 * kMigRows * mig_cap
   float* recv_buf = nullptr;  // 2 * kMigRows * mig_cap
-  unsigned int* d_counts = nullptr;  // [0..1] out, [2..3] in
+  unsigned int* d_counts = nullptr;  // [0..1] out, [2..3] in, [4] escape count summed over all ranks
   unsigned int* h_counts = nullptr;  // pinned mirror
   std::string err;
 
@@ -156,9 +156,9 @@ struct Comm {
     if (e != cudaSuccess) return failc("cudaMalloc(send_buf)", e);
     e = cudaMalloc(&recv_buf, sizeof(float) * 2 * kMigRows * mig_cap);
     if (e != cudaSuccess) return failc("cudaMalloc(recv_buf)", e);
-    e = cudaMalloc(&d_counts, sizeof(unsigned int) * 4);
+    e = cudaMalloc(&d_counts, sizeof(unsigned int) * 8);
     if (e != cudaSuccess) return failc("cudaMalloc(counts)", e);
-    e = cudaMallocHost(&h_counts, sizeof(unsigned int) * 4);
+    e = cudaMallocHost(&h_counts, sizeof(unsigned int) * 8);
     if (e != cudaSuccess) return failc("cudaMallocHost(counts)", e);
     on = true;
     return 0;
@@ -181,6 +181,7 @@ struct Comm {
     }
     r = ncclGroupEnd();
     if (r != ncclSuccess) return fail("ncclGroupEnd(halo)", r);
+    if (int rc = check_async()) return rc;
     if (has_lo) {
       halo_add_kernel<<<(unsigned)((n_lo + 255) / 256), 256, 0, stream>>>(grid + plane * lo_begin, recv_lo, n_lo);
       ++*launches;
@@ -196,10 +197,14 @@ struct Comm {
 
   // Moves leavers to the neighbours and appends arrivals behind `count`.  On return *count
   // includes the arrivals and still includes the tombstoned leavers; *n_dead is their number.
-  int migrate(Soa& p, size_t* count, size_t capacity, const KParams& k, cudaStream_t stream, uint64_t* launches, size_t* n_dead) {
+  // d_escaped: this rank's count of particle-substeps that scattered outside its planes since the last
+  // re-bin; *escaped_all = the sum over ALL ranks, so that every rank takes the same decision about it.
+  int migrate(Soa& p, size_t* count, size_t capacity, const KParams& k, cudaStream_t stream, uint64_t* launches, size_t* n_dead,
+              const unsigned int* d_escaped, unsigned int* escaped_all) {
     *n_dead = 0;
+    *escaped_all = 0;
     if (!on) return 0;
-    cudaError_t e = cudaMemsetAsync(d_counts, 0, sizeof(unsigned int) * 4, stream);
+    cudaError_t e = cudaMemsetAsync(d_counts, 0, sizeof(unsigned int) * 8, stream);
     if (e != cudaSuccess) return failc("memset(counts)", e);
     if (*count) {
       migrate_pack_kernel<<<(unsigned)((*count + 255) / 256), 256, 0, stream>>>(p, *count, k, send_buf, mig_cap, d_counts);
@@ -218,10 +223,13 @@ struct Comm {
     }
     r = ncclGroupEnd();
     if (r != ncclSuccess) return fail("ncclGroupEnd(counts)", r);
-    e = cudaMemcpyAsync(h_counts, d_counts, sizeof(unsigned int) * 4, cudaMemcpyDeviceToHost, stream);
+    r = ncclAllReduce(d_escaped, d_counts + 4, 1, ncclUint32, ncclSum, comm, stream);
+    if (r != ncclSuccess) return fail("ncclAllReduce(escaped)", r);
+    e = cudaMemcpyAsync(h_counts, d_counts, sizeof(unsigned int) * 8, cudaMemcpyDeviceToHost, stream);
     if (e != cudaSuccess) return failc("memcpy(counts)", e);
     e = cudaStreamSynchronize(stream);
     if (e != cudaSuccess) return failc("sync(counts)", e);
+    *escaped_all = h_counts[4];
     const size_t out_lo = has_lo ? h_counts[0] : 0, out_hi = has_hi ? h_counts[1] : 0;
     const size_t in_lo = has_lo ? h_counts[2] : 0, in_hi = has_hi ? h_counts[3] : 0;
     if (out_lo > mig_cap || out_hi > mig_cap || in_lo > mig_cap || in_hi > mig_cap) {

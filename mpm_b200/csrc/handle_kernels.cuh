@@ -124,10 +124,11 @@ __global__ void generate_block_kernel(Soa p, unsigned long long first_id, unsign
     if (slot >= capacity) return;
   }
   float* c = p.col(slot);
+  // individually rounded operations: bit-identical to the numpy mirror in tests/oracle_lib.py
   float v[3] = {0.f, 0.f, 0.f};
   if (st.shear != 0.f) {
-    v[0] = st.shear * (x[1] - 0.5f);
-    v[2] = 0.3f * st.shear * (x[0] - 0.5f);
+    v[0] = __fmul_rn(st.shear, __fsub_rn(x[1], 0.5f));
+    v[2] = __fmul_rn(__fmul_rn(0.3f, st.shear), __fsub_rn(x[0], 0.5f));
   }
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
@@ -139,7 +140,8 @@ __global__ void generate_block_kernel(Soa p, unsigned long long first_id, unsign
     float f = (e % 4 == 0) ? 1.0f : 0.0f;
     if (st.f_noise != 0.f) {
       const uint32_t h = lowbias32((uint32_t)(id * 9ull + (unsigned long long)e) ^ (seed_hash * 0x9e3779b9u + 77u));
-      f += st.f_noise * ((float)(h >> 8) * (2.0f / 16777216.0f) - 1.0f);
+      const float u = __fsub_rn(__fmul_rn((float)(h >> 8), 2.0f / 16777216.0f), 1.0f);
+      f = __fadd_rn(f, __fmul_rn(st.f_noise, u));
     }
     c[(SF + e) * kTile] = f;
     c[(SC + e) * kTile] = 0.0f;

@@ -210,11 +210,18 @@ const char* const kStageNames[MPM_STAGE_COUNT] = {"mpm:sort", "mpm:reset", "mpm:
 
 // NVTX range per stage (visible in nsys / ncu timelines); with timing on also CUDA events + a host
 // synchronisation, which serialises the stages — profiling only
+bool nvtx_on() {
+  static const bool on = [] {
+    const char* e = getenv("MPM_B200_NVTX");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
 struct StageTimer {
   MpmSim* s;
   int stage;
   StageTimer(MpmSim* s_, int st) : s(s_), stage(st) {
-    nvtxRangePushA(kStageNames[st]);
+    if (nvtx_on()) nvtxRangePushA(kStageNames[st]);
     if (s->timing) cudaEventRecord(s->ev[0], s->stream);
   }
   ~StageTimer() {
@@ -225,7 +232,7 @@ struct StageTimer {
       cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]);
       s->stage_ms[stage] += ms;
     }
-    nvtxRangePop();
+    if (nvtx_on()) nvtxRangePop();
   }
 };
 
@@ -274,14 +281,16 @@ int do_sort(MpmSim* sim, bool partial = false, bool keys_ready = false) {
   size_t n_dead = 0;
   if (sim->comm.active()) {  // leavers out (tombstoned), arrivals appended, before the re-bin
     // particles whose stencil left the planes held here since the last re-bin lost mass on the grid:
-    // that is a configuration error (ghost width / re-bin cadence too small for the velocities)
-    CK(cudaMemcpyAsync(sim->h_diag, sim->d_diag, sizeof(DeviceDiag), cudaMemcpyDeviceToHost, sim->stream));
-    CK(cudaMemsetAsync(&sim->d_diag->escaped, 0, sizeof(unsigned int), sim->stream));
-    if (sim->comm.migrate(sim->soa[sim->cur], &sim->count, sim->capacity, sim->k, sim->stream, &sim->launches, &n_dead))
+    // that is a configuration error (ghost width / re-bin cadence too small for the velocities), and
+    // every rank must stop for it, not only the one that saw it
+    unsigned int escaped = 0;
+    if (sim->comm.migrate(sim->soa[sim->cur], &sim->count, sim->capacity, sim->k, sim->stream, &sim->launches, &n_dead, &sim->d_diag->escaped,
+                          &escaped))
       return fail(sim, "particle migration failed: %s", sim->comm.error());
-    if (sim->h_diag->escaped)  // (migrate synchronised the stream)
-      return fail(sim, "%u particle-substeps scattered outside the %d ghost plane(s) of slab [%d,%d) since the last re-bin: "
-                       "raise MpmParams.ghost or lower sort_every", sim->h_diag->escaped, sim->ghost, sim->k.x_own_begin, sim->k.x_own_end);
+    CK(cudaMemsetAsync(&sim->d_diag->escaped, 0, sizeof(unsigned int), sim->stream));
+    if (escaped)
+      return fail(sim, "%u particle-substeps (all ranks) scattered outside the %d ghost plane(s) of their slab since the last re-bin; "
+                       "this rank holds [%d,%d): raise MpmParams.ghost or lower sort_every", escaped, sim->ghost, sim->k.x_own_begin, sim->k.x_own_end);
   }
   const size_t n = sim->count;
   if (n == 0) return 0;

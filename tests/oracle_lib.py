@@ -256,6 +256,26 @@ def dense_block_positions(count, seed=1234, lo=0.1, hi=0.9, first_id=0):
     return out
 
 
+def dense_block_stress(p, seed=1234, shear=0.0, f_noise=0.0, first_id=0):
+    """mpm_generate_dense_block_stressed (mpm_b200/csrc/handle_kernels.cuh) on the host, bit for bit:
+    v = shear * (y - 0.5, 0, 0.3 (x - 0.5)), F = I + f_noise * u, u in [-1, 1) from the counter hash."""
+    n = p.shape[0]
+    f32 = np.float32
+    if shear:
+        p["v"][:, 0] = f32(shear) * (p["x"][:, 1] - f32(0.5))
+        p["v"][:, 2] = (f32(0.3) * f32(shear)) * (p["x"][:, 0] - f32(0.5))
+    if f_noise:
+        ids = np.arange(first_id, first_id + n, dtype=np.uint64)
+        with np.errstate(over="ignore"):
+            salt = lowbias32(np.uint32(seed)) * np.uint32(0x9E3779B9) + np.uint32(77)
+            for e in range(9):
+                h = lowbias32(((ids * np.uint64(9) + np.uint64(e)) & np.uint64(0xFFFFFFFF)).astype(np.uint32) ^ salt)
+                u = (h >> np.uint32(8)).astype(f32) * f32(2.0 / 16777216.0) - f32(1.0)
+                r, c = divmod(e, 3)  # the device numbers the entries row-major; the AoS record is column-major
+                p["F"][:, 3 * c + r] = p["F"][:, 3 * c + r] + f32(f_noise) * u
+    return p
+
+
 def sphere_positions(count_density, size, position, rng):
     """Stand-in for sphere.obj (LFS stub in the reference checkout): rejection-sample the ball of
     diameter `size` whose bounding box has its low corner at `position` (src/mpm.cu:331-394)."""

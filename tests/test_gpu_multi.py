@@ -13,10 +13,14 @@ pytestmark = pytest.mark.gpu
 DT = 1e-4
 
 
-def _two_gpus():
+def _gpus():
     import torch
 
-    return torch.cuda.device_count() >= 2
+    return torch.cuda.device_count()
+
+
+def _two_gpus():
+    return _gpus() >= 2
 
 
 def _run_ranks(N, mats, kind, p, slabs, steps, sort_every, mode=0, pipeline=0):
@@ -98,7 +102,7 @@ def test_halo_sum_is_identical_on_both_ranks():
 
     def work(r):
         try:
-            sim = mpm_b200.Sim(N, DT, mats, model=ol.SNOW, x_begin=slabs[r][0], x_end=slabs[r][1], device=r, capacity=len(p))
+            sim = mpm_b200.Sim(N, DT, mats, model=ol.SNOW, sort_every=100, x_begin=slabs[r][0], x_end=slabs[r][1], device=r, capacity=len(p))
             sim.attach_comm(uid, r, 2)
             mine = np.where(own == r)[0]
             sim.upload_with_ids(np.ascontiguousarray(p[mine]), mine.astype(np.uint32))
@@ -119,3 +123,80 @@ def test_halo_sum_is_identical_on_both_ranks():
     full = np.concatenate([grids[0][:16], grids[1][1:]], 0)
     scale = np.abs(go[..., :3]).max()
     assert np.abs(full[..., :3] - go[..., :3]).max() < 1e-5 * scale
+
+
+@pytest.mark.parametrize("ranks", [3, 4])
+@pytest.mark.parametrize("kind", [ol.SNOW, ol.FIXED_COROTATED])
+def test_n_slabs_bidirectional_migration(ranks, kind):
+    """3 and 4 slabs: middle ranks with two neighbours, particles crossing every slab boundary in both
+    directions (shear flow: +x above the mid-plane, -x below), 9-bit radix digits where the slab's key
+    range asks for them; per-particle state against the single-GPU run and the checker."""
+    if _gpus() < ranks:
+        pytest.skip(f"needs {ranks} GPUs")
+    import mpm_b200
+    from mpm_b200 import slabs as sl
+
+    N, steps, P = 48, 48, 150_000
+    p, mats = scenes.dense_block(P, N, kind=kind, shear=40.0, f_noise=0.01)
+    slabs = sl.balanced_slabs(N, ranks, 0.1, 0.9)
+    own0 = sl.owner(p["x"][:, 0], N, slabs)
+    merged, counts = _run_ranks(N, mats, kind, p, slabs, steps, sort_every=4)
+    own1 = sl.owner(merged["x"][:, 0], N, slabs)
+    for r in range(ranks - 1):   # both directions across every boundary
+        assert ((own0 == r) & (own1 == r + 1)).sum() > 10, r
+        assert ((own0 == r + 1) & (own1 == r)).sum() > 10, r
+    single = mpm_b200.Sim(N, DT, mats, model=kind, sort_every=4)
+    single.upload(p)
+    single.advance(steps)
+    ref_gpu = single.download()
+    ref, _ = ol.advance(p.copy(), mats, DT, N, kind, steps)
+    dx = 1.0 / N
+    vmax = np.abs(ref["v"]).max()
+    for name, other in (("single-GPU", ref_gpu), ("checker", ref)):
+        pos = np.abs(merged["x"].astype(np.float64) - other["x"]).max() / dx
+        vel = np.abs(merged["v"].astype(np.float64) - other["v"]).max()
+        assert pos < 1e-3 and vel < 1e-3 * vmax, (name, pos, vel)
+
+
+def test_escape_beyond_the_ghost_planes_is_reported():
+    """a particle that drifts more than `ghost` cells out of its slab between re-bins used to
+    lose mass silently.  Now the re-bin fails with a message that names the remedy."""
+    if not _two_gpus():
+        pytest.skip("needs 2 GPUs")
+    import mpm_b200
+    from mpm_b200 import slabs as sl
+
+    N = 32
+    p, mats = scenes.dense_block(40_000, N, kind=ol.FIXED_COROTATED)
+    p["v"][:, 0] = 80.0   # 0.256 cells per substep: 2.5 cells between re-bins 10 substeps apart
+    slabs = [(0, 16), (16, 32)]
+    own = sl.owner(p["x"][:, 0], N, slabs)
+    uid = mpm_b200.comm_unique_id()
+    msgs = [None, None]
+
+    def work(r):
+        sim = mpm_b200.Sim(N, DT, mats, model=ol.FIXED_COROTATED, sort_every=10, x_begin=slabs[r][0], x_end=slabs[r][1], device=r,
+                           capacity=len(p))
+        sim.attach_comm(uid, r, 2)
+        mine = np.where(own == r)[0]
+        sim.upload_with_ids(np.ascontiguousarray(p[mine]), mine.astype(np.uint32))
+        try:
+            sim.advance(11)
+            msgs[r] = "no error"
+        except mpm_b200.MpmError as e:
+            msgs[r] = str(e)
+
+    th = [threading.Thread(target=work, args=(r,)) for r in range(2)]
+    [t.start() for t in th]
+    [t.join(timeout=300) for t in th]
+    assert "ghost" in msgs[0] and "scattered outside" in msgs[0], msgs
+
+
+def test_slab_handles_need_a_rebin_cadence():
+    if not _two_gpus():
+        pytest.skip("needs 2 GPUs")
+    import mpm_b200
+
+    sim = mpm_b200.Sim(32, DT, ol.make_material(2e-6), sort_every=0, x_begin=0, x_end=16, capacity=1000)
+    with pytest.raises(mpm_b200.MpmError, match="sort_every"):
+        sim.attach_comm(mpm_b200.comm_unique_id(), 0, 2)

@@ -17,7 +17,7 @@ if sys.argv[1] == "build":
         b.build(force=True, defines=defines, out=out)
         print("built", out, defines)
 else:
-    extra = os.environ.get("AB_BENCH_ARGS", "--steps 16 --warmup 6 --no-e2e --no-cpu").split()
+    extra = os.environ.get("AB_BENCH_ARGS", "--steps 16 --warmup 8 --no-e2e --no-cpu --no-extras").split()
     for name in sys.argv[2:]:
         env = dict(os.environ, MPM_B200_LIB=os.path.join(VAR, f"libmpm_{name}.so"))
         r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py")] + extra, env=env, capture_output=True, text=True)
