@@ -23,7 +23,7 @@ def lib():
         L.mpmh_scene_load.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.c_int]
         L.mpmh_scene_free.argtypes = [_vp]
         L.mpmh_scene_free.restype = None
-        for n in ("mpmh_n_materials", "mpmh_n_objects", "mpmh_init_cuda", "mpmh_sync_device"):
+        for n in ("mpmh_n_materials", "mpmh_n_objects", "mpmh_init_cuda", "mpmh_sync_device", "mpmh_grid_size"):
             getattr(L, n).argtypes = [_vp]
         L.mpmh_get_materials.argtypes = [_vp, _vp]
         L.mpmh_object_count.restype = ctypes.c_size_t
@@ -86,6 +86,14 @@ class Scene:
     @property
     def n_objects(self):
         return lib().mpmh_n_objects(self._h)
+
+    @property
+    def N(self):
+        return lib().mpmh_grid_size(self._h)
+
+    @property
+    def full_count(self):
+        return lib().mpmh_full_count(self._h)
 
     def object_counts(self):
         return [lib().mpmh_object_count(self._h, o) for o in range(self.n_objects)]

@@ -43,6 +43,7 @@ MpmhScene* mpmh_scene_load(int argc, char** argv, int seed) {
 }
 void mpmh_scene_free(MpmhScene* s) { delete s; }
 
+int mpmh_grid_size(const MpmhScene* s) { return (int)s->flags.N; }
 int mpmh_n_materials(const MpmhScene* s) { return (int)s->materials.size(); }
 void mpmh_get_materials(const MpmhScene* s, float* out7) { std::memcpy(out7, s->materials.data(), s->materials.size() * sizeof(MaterialModel)); }
 int mpmh_n_objects(const MpmhScene* s) { return (int)s->sim->objects.size(); }

@@ -34,10 +34,14 @@ struct TriMesh {
 
 inline bool is_lfs_stub(const std::string& path) {
   std::ifstream f(path);
-  if (!f) return true;
+  if (!f) return false;
   std::string first;
   std::getline(f, first);
   return first.rfind("version https://git-lfs", 0) == 0;
+}
+// the four meshes the reference's scenes name (all Git-LFS pointers in its checkout)
+inline bool is_reference_mesh_name(const std::string& filename) {
+  return filename == "sphere.obj" || filename == "cube.obj" || filename == "rubber_duck.obj" || filename == "stanford_bunny.obj";
 }
 
 // `v x y z [w]`, `f` corners as i, i/t, i/t/n or i//n (1-based; negative = relative to the end);
@@ -163,11 +167,15 @@ inline TriMesh stand_in_for(const std::string& filename) {
   return make_ellipsoid(1.0f, 1.0f, 1.0f);
 }
 
-// the file's mesh, or its stand-in when the file is an LFS stub / missing; *substituted says which
+// The file's mesh, or a procedural stand-in when the file is a Git-LFS pointer, or when it is absent
+// AND carries the name of one of the reference's own meshes (whose geometry this repository cannot
+// ship); any other missing or unreadable file is an error.  *substituted says which.
 inline bool load_mesh_or_stand_in(const std::string& path, TriMesh& m, bool* substituted, std::string* err) {
-  if (is_lfs_stub(path)) {
-    const size_t slash = path.find_last_of('/');
-    m = stand_in_for(slash == std::string::npos ? path : path.substr(slash + 1));
+  const size_t slash = path.find_last_of('/');
+  const std::string name = slash == std::string::npos ? path : path.substr(slash + 1);
+  const bool missing = !std::ifstream(path).good();
+  if (is_lfs_stub(path) || (missing && is_reference_mesh_name(name))) {
+    m = stand_in_for(name);
     if (substituted) *substituted = true;
     return true;
   }

@@ -1,9 +1,11 @@
 // Command-line options of the simulator: the same flags, defaults and derived fields as the
 // reference's CLIOptions (include/options.h:6-53), parsed without cxxopts.
-// Accepted forms: --name value, --name=value.  A parse error prints a message and exits with
-// status 1, like the reference (options.h:48-51).  Extensions (not in the reference, all optional):
+// Accepted forms: --name value, --name=value, and for the grid size the reference's own spelling
+// `-N value` (cxxopts turns the one-letter option name "N" into a SHORT option, include/cxxopts.h:1457,
+// 1634-1662, so the reference's README commands say `-N 16`); `-N16`, `-N=16` and `--N 16` are taken too.
+// A parse error prints a message and exits with status 1, like the reference (options.h:48-51).  Extensions (not in the reference, all optional):
 // --steps (stop after this many substeps; the reference loops until killed), --svd exact|fast,
-// --model snow|fixed_corotated (the compile-time MaterialModel alias of include/mpm.cuh:25 as data),
+// --model snow|fixed_corotated|jelly (the compile-time MaterialModel alias of include/mpm.cuh:25 as data),
 // --sort-every, --rebin-permille, --sync-every, --frame-rate.
 #pragma once
 #include <cstdint>
@@ -61,6 +63,19 @@ struct CLIOptions {
     std::map<std::string, std::string> kv;
     for (int i = 1; i < argc; ++i) {
       std::string a = argv[i];
+      if (a.rfind("-N", 0) == 0 && a.rfind("--", 0) != 0) {  // the short option of the reference
+        std::string val = a.substr(2);
+        if (!val.empty() && val[0] == '=') val = val.substr(1);
+        if (val.empty()) {
+          if (i + 1 >= argc) {
+            err = "Option 'N' is missing an argument";
+            return false;
+          }
+          val = argv[++i];
+        }
+        kv["N"] = val;
+        continue;
+      }
       if (a.rfind("--", 0) != 0) {
         err = "Unexpected argument '" + a + "'";
         return false;
@@ -108,7 +123,7 @@ struct CLIOptions {
       err = "Argument could not be parsed";
       return false;
     }
-    if (N == 0 || (svd != "exact" && svd != "fast") || (model != "snow" && model != "fixed_corotated")) {
+    if (N == 0 || sync_every == 0 || (svd != "exact" && svd != "fast") || (model != "snow" && model != "fixed_corotated" && model != "jelly")) {
       err = "Argument out of range";
       return false;
     }

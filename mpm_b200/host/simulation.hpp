@@ -126,7 +126,8 @@ class Simulation {
     MpmParams p{};
     p.dt = par.dt;
     p.N = par.N;
-    p.model = opts_.model == "fixed_corotated" ? MPM_MODEL_FIXED_COROTATED : MPM_MODEL_SNOW;  // mpm.cuh:25: MaterialModel = MMSnow
+    // mpm.cuh:25: MaterialModel = MMSnow; the other classes of MaterialModel.cuh by --model
+    p.model = opts_.model == "fixed_corotated" ? MPM_MODEL_FIXED_COROTATED : opts_.model == "jelly" ? MPM_MODEL_JELLY : MPM_MODEL_SNOW;
     p.svd_mode = opts_.svd == "fast" ? MPM_SVD_FAST : MPM_SVD_EXACT;
     p.sort_every = opts_.sort_every;
     p.rebin_permille = opts_.rebin_permille;
@@ -137,17 +138,33 @@ class Simulation {
     uploadActive();
   }
 
-  // src/mpm.cu:323-329, plus the lifetime handling described above
+  // src/mpm.cu:323-329, plus the lifetime handling described above.  Like the reference's advance()
+  // this returns before the GPU has done anything; here the substeps are also handed to the device
+  // in batches (at most kBatch, flushed by syncDevice / syncPositions / a change of the active set):
+  // within one mpm_advance call the kernels hand the next P2G's affine matrix over (MPM_PIPE_HANDOVER).
+  static constexpr int kBatch = 20;  // the reference's sync cadence, src/main.cu:99
   void advance() {
     if (!sim_) throw std::runtime_error("advance() before initCuda()");
-    if (activeSetChanged()) applyLifetimes();
-    check(mpm_advance(sim_, 1));
+    if (activeSetChanged()) {
+      flush();
+      applyLifetimes();
+    }
+    ++pending_;
     t += par.dt;
+    if (pending_ >= kBatch) flush();
+  }
+  void flush() {
+    if (sim_ && pending_) {
+      const int n = pending_;
+      pending_ = 0;
+      check(mpm_advance(sim_, n));
+    }
   }
 
   // src/mpm.cu:209-211, 288-306: device -> per-object host vectors (blocking)
   void syncDevice() {
     if (!sim_) return;
+    flush();
     size_t n = 0;
     host_.resize(uploaded_count());
     check(mpm_download_particles_aos(sim_, host_.data(), host_.size(), &n));
@@ -158,6 +175,7 @@ class Simulation {
 
   // positions only (12 B/particle) in upload order (= getActiveParticleList order until an object is appended): what a viewer needs
   void syncPositions(std::vector<float>& xyz) {
+    flush();
     xyz.resize(3 * uploaded_count());
     size_t n = 0;
     if (sim_ && !xyz.empty()) check(mpm_download_positions(sim_, xyz.data(), xyz.size() / 3, &n));
@@ -182,7 +200,10 @@ class Simulation {
     return particles_all_;
   }
 
-  MpmSim* handle() { return sim_; }
+  MpmSim* handle() {
+    flush();
+    return sim_;
+  }
 
   // src/mpm.cu:348-394: rejection sampling in the bounding box, glibc rand() in x, y, z order,
   // 2048 points per batch, a point is kept when its winding number truncates to 1
@@ -219,6 +240,7 @@ class Simulation {
  private:
   CLIOptions opts_;
   MpmSim* sim_ = nullptr;
+  int pending_ = 0;  // substeps advance() has accepted and not yet handed to the device
   std::vector<size_t> uploaded_;  // object indices on the device, in upload order
   std::vector<Particle> particles_all_, host_;
 

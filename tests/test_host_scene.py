@@ -24,9 +24,39 @@ def test_options_defaults_forms_and_errors():
     assert s.n_objects == 2 and len(s.materials) == 1
     host.Scene("--scene", os.path.join(SCENES, "rubber_duck.toml"), "--N", "16", "--particle-count", "2000", "--model", "fixed_corotated",
                "--svd=fast", "--rebin-permille", "50", "--sort-every", "0")
-    for bad in (["--bogus", "1"], ["--N"], ["--N", "abc"], ["--N", "-4"], ["positional"], ["--model", "jelly"], ["--svd", "sloppy"]):
+    for bad in (["--bogus", "1"], ["--N"], ["--N", "abc"], ["--N", "-4"], ["positional"], ["--model", "rubber"], ["--svd", "sloppy"], ["-N"],
+                ["-N", "x"], ["-M", "16"], ["--sync-every", "0"]):
         r = subprocess.run([CLI] + bad, capture_output=True, text=True)
         assert r.returncode == 1 and r.stdout.strip(), bad  # message + exit(1), like options.h:48-51
+
+
+def test_grid_size_short_option_like_the_reference():
+    """The reference registers the option "N"; cxxopts makes a one-letter name the SHORT option, so its
+    README says `-N 16` (README.md:14-16).  All spellings give the same scene."""
+    host.lib()
+    scene = os.path.join(SCENES, "rubber_duck.toml")
+    counts = []
+    for form in (["-N", "16"], ["-N16"], ["-N=16"], ["--N", "16"], ["--N=16"]):
+        s = host.Scene("--scene", scene, *form, "--particle-count", "10000")
+        assert s.N == 16
+        counts.append(s.full_count)
+    assert len(set(counts)) == 1
+
+
+@pytest.mark.parametrize("line", ["--scene scenes/rubber_duck.toml -N 16 --particle-count 10000",
+                                  "--scene scenes/liquid_bunny.toml -N 32 --particle-count 1000000",
+                                  "--scene scenes/snowman.toml -N 64 --particle-count 500000"])
+def test_readme_command_lines_parse_verbatim(line):
+    """The three example commands of the reference's README (README.md:14-16), argument for argument
+    (run from the repository root, like ./docker_run.sh does from the reference's)."""
+    host.lib()
+    cwd = os.getcwd()
+    os.chdir(ROOT)
+    try:
+        s = host.Scene(*line.split())
+    finally:
+        os.chdir(cwd)
+    assert s.N == int(line.split()[3]) and s.n_objects >= 1 and s.full_count > 100
     with pytest.raises(host.MpmError):
         host.Scene("--scene", "/nonexistent/scene.toml")
 
