@@ -124,7 +124,7 @@ __global__ void generate_block_kernel(Soa p, unsigned long long first_id, unsign
     if (slot >= capacity) return;
   }
   float* c = p.col(slot);
-  // individually rounded operations: bit-identical to the numpy mirror in tests/oracle_lib.py
+  // individually rounded operations: bit-identical to the numpy mirror the tests keep of this generator
   float v[3] = {0.f, 0.f, 0.f};
   if (st.shear != 0.f) {
     v[0] = __fmul_rn(st.shear, __fsub_rn(x[1], 0.5f));
