@@ -137,13 +137,15 @@ __device__ __forceinline__ void g2p_gather27(const float4* __restrict__ tp, long
       s1 = fma2(WZD[2], pack2(g2.x, g2.y), s1);
       s0z = fmaf(w[2][2], g2.z, s0z);
       s1z = fmaf(wzd[2], g2.z, s1z);
+      // (forming these products as packed pairs from pre-duplicated weights saves the dup moves but costs
+      // 12 registers: 2.02 -> 2.24 ms, profiles/r02_ab3_g2p.txt)
       const float wij = w[0][i] * w[1][j], wdx = wxd[i] * w[1][j], wdy = w[0][i] * wyd[j];
-      const f2 WIJ = dup2(wij);
+      const f2 WIJ = dup2(wij), WDX = dup2(wdx), WDY = dup2(wdy);
       Vxy = fma2(WIJ, s0, Vxy);
       vz = fmaf(wij, s0z, vz);
-      B0xy = fma2(dup2(wdx), s0, B0xy);
+      B0xy = fma2(WDX, s0, B0xy);
       B0z = fmaf(wdx, s0z, B0z);
-      B1xy = fma2(dup2(wdy), s0, B1xy);
+      B1xy = fma2(WDY, s0, B1xy);
       B1z = fmaf(wdy, s0z, B1z);
       B2xy = fma2(WIJ, s1, B2xy);
       B2z = fmaf(wij, s1z, B2z);
