@@ -459,7 +459,8 @@ inline bool outside(const int base[3], int N) {  // src/mpm.cu:31-35, :127-131
 
 // particleToGrid, src/mpm.cu:14-74 + MLS_APIC_Scheme::p2g_prepare_particle / p2g_node_contribution,
 // include/TransferScheme.h:66-100.  grid: N^3 float4 (px,py,pz,m), idx = N*N*i + N*j + k.
-void p2g(const Particle* ps, size_t count, const Material* mats, const Params& par, int kind, float* grid) {
+// magnitudes: accumulate w (|m v| + sum_k |A_ck d_k|) instead (the per-node error scale of SURVEY.md 8(c)(3))
+void p2g(const Particle* ps, size_t count, const Material* mats, const Params& par, int kind, float* grid, bool magnitudes = false) {
   const int N = (int)par.N;
   const float dinv = dinv_scalar(par.dx_inv);
 #pragma omp parallel for schedule(static)
@@ -497,6 +498,9 @@ void p2g(const Particle* ps, size_t count, const Material* mats, const Params& p
             out[c] = weight * (p.v[c] * m.particleMass + ad);
           }
           out[3] = weight * m.particleMass;
+          if (magnitudes)  // the terms' magnitudes: m v and A d may cancel, a rounding error does not
+            for (int c = 0; c < 3; ++c)
+              out[c] = weight * (std::fabs(p.v[c] * m.particleMass) + std::fabs(A.a[c][0] * d0) + std::fabs(A.a[c][1] * d1) + std::fabs(A.a[c][2] * d2));
           float* cell = grid + 4 * ((size_t)N * N * ig + (size_t)N * jg + kg);
           for (int c = 0; c < 4; ++c) {
 #pragma omp atomic
@@ -693,6 +697,12 @@ void oracle_reset_grid(float* grid, uint32_t N) { std::memset(grid, 0, sizeof(fl
 void oracle_p2g(const void* particles, size_t count, const float* mats, float dt, uint32_t N, int kind, float* grid) {
   Params par(dt, N);
   p2g((const Particle*)particles, count, (const Material*)mats, par, kind, grid);
+}
+// sum over particles of the magnitudes of the terms of each contribution, per node and channel: what a
+// per-node P2G error is measured against
+void oracle_p2g_magnitudes(const void* particles, size_t count, const float* mats, float dt, uint32_t N, int kind, float* grid) {
+  Params par(dt, N);
+  p2g((const Particle*)particles, count, (const Material*)mats, par, kind, grid, true);
 }
 void oracle_grid_update(float* grid, float dt, uint32_t N) {
   Params par(dt, N);

@@ -149,6 +149,15 @@ def p2g(p, mats, dt, N, kind, grid=None):
     return grid
 
 
+def p2g_magnitudes(p, mats, dt, N, kind):
+    """Sum over particles of |contribution| per node and channel (the scale of a per-node P2G error)."""
+    grid = new_grid(N)
+    mats = np.ascontiguousarray(mats, np.float32)
+    lib().oracle_p2g_magnitudes(p.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(p.shape[0]), _f(mats), ctypes.c_float(dt),
+                                ctypes.c_uint32(N), ctypes.c_int(kind), _f(grid))
+    return grid
+
+
 def grid_update(grid, dt, N):
     lib().oracle_grid_update(_f(grid), ctypes.c_float(dt), ctypes.c_uint32(N))
     return grid

@@ -24,13 +24,13 @@ def two_spheres(N=32, density=500000.0, seed=1, kind=ol.SNOW, perturb=True):
     return p, mats
 
 
-def dense_block(count, N, density=None, seed=1234, kind=ol.FIXED_COROTATED, shear=0.0, f_noise=0.0, first_id=0):
+def dense_block(count, N, density=None, seed=1234, kind=ol.FIXED_COROTATED, shear=0.0, f_noise=0.0, first_id=0, lo=0.1, hi=0.9):
     """SURVEY.md 8(d) configs 4 / 5 at any size: uniform block in [0.1,0.9]^3, fixed-corotated or the
     snowman's snow; optionally under stress (mpm_generate_dense_block_stressed)."""
-    x = ol.dense_block_positions(count, seed, first_id=first_id)
+    x = ol.dense_block_positions(count, seed, lo, hi, first_id=first_id)
     p = ol.new_particles(x)
     ol.dense_block_stress(p, seed, shear, f_noise, first_id)
-    dens = density if density is not None else count / 0.512
+    dens = density if density is not None else count / (hi - lo) ** 3
     if kind == ol.SNOW:
         mats = ol.make_material(1.0 / dens, 700.0, 1.4e5, 0.2, 10.0, 0.975, 1.0075)  # scenes/snowman.toml
     else:
