@@ -1,7 +1,7 @@
 // mpm_b200_cli: the reference's main() (src/main.cu:22-115) over the B200-native substep.
 // Same flags (options.hpp), same scene files, same loop: advance(); every 20 substeps syncDevice();
 // with --save-dir, every 1 / 240 / dt substeps a surface mesh meshes/mesh_%05d.obj and a particle
-// dump particles/particles_%d.pda.  Headless (the GLFW viewer is out of scope); --steps bounds the
+// dump particles/particles_%d.bgeo (--particle-format pda: Partio's ASCII flavour).  Headless (the GLFW viewer is out of scope); --steps bounds the
 // loop, which the reference runs until it is killed.
 #include <sys/stat.h>
 
@@ -51,7 +51,7 @@ int main(int argc, char* argv[]) {
         mesher.computeMesh(ss.str(), simulation.getActiveParticleList());
         ss.str("");
         ss.clear();
-        ss << flags.save_dir << "/particles/particles_" << frame_id << ".pda";
+        ss << flags.save_dir << "/particles/particles_" << frame_id << "." << flags.particle_format;
         writer.writeParticles(ss.str(), simulation.getActiveParticleList());
         frame_id++;
       }

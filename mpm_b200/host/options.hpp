@@ -43,7 +43,7 @@ struct CLIOptions {
   u32 rebin_permille = 0;  // MpmParams.rebin_permille
   u32 sync_every = 20;  // src/main.cu:99
   u32 frame_rate = 240; // src/main.cu:8
-  std::string particle_format = "pda";
+  std::string particle_format = "bgeo";  // bgeo (the reference, src/main.cu:109) or pda (Partio ASCII)
 
   CLIOptions() { derive(); }
   CLIOptions(int argc, char* argv[]) {
@@ -123,7 +123,7 @@ struct CLIOptions {
       err = "Argument could not be parsed";
       return false;
     }
-    if (N == 0 || sync_every == 0 || (svd != "exact" && svd != "fast") || (model != "snow" && model != "fixed_corotated" && model != "jelly")) {
+    if (N == 0 || sync_every == 0 || (particle_format != "bgeo" && particle_format != "pda") || (svd != "exact" && svd != "fast") || (model != "snow" && model != "fixed_corotated" && model != "jelly")) {
       err = "Argument out of range";
       return false;
     }

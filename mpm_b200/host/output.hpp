@@ -5,43 +5,124 @@
 // mesh_grid^3 lattice, vertices scaled by voxel_dx, igl::writeOBJ).
 //
 // Partio and libigl are not available to this build, so:
-//   * particles are written as Partio's ASCII format (.pda: ATTRIBUTES / TYPES / NUMBER_OF_PARTICLES
-//     / BEGIN DATA) with the same four attributes; the reference writes the binary .bgeo flavour of
-//     the same attribute table;
+//   * particles are written in Partio's own file formats, chosen by the file extension like
+//     Partio::write does: .bgeo (the reference's choice, src/main.cu:109: Houdini's classic binary
+//     geometry, version 5, big-endian: header, attribute dictionary, one (x, y, z, 1) + attributes record
+//     per point, one particle-system primitive) and .pda (Partio's ASCII table).  Same four attributes
+//     in the same order.  Written from the format description; with Partio absent the bytes are not
+//     pinned against the reference's output.
 //   * the iso-surface is extracted by marching tetrahedra (six tetrahedra per lattice cube around
 //     the 0-6 diagonal) instead of libigl's GPL marching-cubes tables: same field, same iso-level,
 //     same lattice, a different (finer) triangulation.  The reference has no golden meshes; the
-//     tests compare enclosed volume and closedness.  --laplacian_smooth and --mesh-face-count
-//     (igl::decimate) are accepted and ignored with a warning.
+//     tests compare enclosed volume and closedness.
+//   * --laplacian_smooth and --mesh-face-count (mesh_builder.h:196-211) are mesh_ops.hpp.
 #pragma once
 #include <cmath>
+#include <cstdint>
 #include <cstdio>
+#include <cstring>
 #include <iostream>
 #include <string>
 #include <unordered_map>
 #include <vector>
 
 #include "mesh.hpp"
+#include "mesh_ops.hpp"
 #include "simulation.hpp"
 
 namespace mpmh {
 
 class ParticleWriter {
  public:
+  // format by extension, like Partio::write: .bgeo (binary) or anything else = .pda (ASCII)
   bool writeParticles(const std::string& filepath, const std::vector<Particle>& particles) const {
-    FILE* f = std::fopen(filepath.c_str(), "w");
+    const bool bgeo = filepath.size() >= 5 && filepath.compare(filepath.size() - 5, 5, ".bgeo") == 0;
+    FILE* f = std::fopen(filepath.c_str(), bgeo ? "wb" : "w");
     if (!f) {
       std::cout << "Warning: Particles could not be written to " << filepath << std::endl;
       return false;
     }
+    if (bgeo) write_bgeo(f, particles); else write_pda(f, particles);
+    std::fclose(f);
+    return true;
+  }
+
+ private:
+  static void write_pda(FILE* f, const std::vector<Particle>& particles) {
     std::fprintf(f, "ATTRIBUTES\n id position velocity radius\nTYPES\n I V V R\nNUMBER_OF_PARTICLES: %zu\nBEGIN DATA\n", particles.size());
     int i = 0;
     for (const Particle& p : particles) {
       std::fprintf(f, "%d %.9g %.9g %.9g %.9g %.9g %.9g %.9g\n", i, p.x[0], p.x[1], p.x[2], p.v[0], p.v[1], p.v[2], 0.1f);
       i++;
     }
-    std::fclose(f);
-    return true;
+  }
+  // big-endian scalars
+  static void be32(FILE* f, uint32_t v) {
+    const unsigned char b[4] = {(unsigned char)(v >> 24), (unsigned char)(v >> 16), (unsigned char)(v >> 8), (unsigned char)v};
+    std::fwrite(b, 1, 4, f);
+  }
+  static void be16(FILE* f, uint16_t v) {
+    const unsigned char b[2] = {(unsigned char)(v >> 8), (unsigned char)v};
+    std::fwrite(b, 1, 2, f);
+  }
+  static void bef(FILE* f, float v) {
+    uint32_t u;
+    std::memcpy(&u, &v, 4);
+    be32(f, u);
+  }
+  static void hstr(FILE* f, const char* s) {
+    const size_t n = std::strlen(s);
+    be16(f, (uint16_t)n);
+    std::fwrite(s, 1, n, f);
+  }
+  // attribute dictionary entry: name, size, Houdini type (0 float, 1 int, 4 index, 5 vector), defaults
+  static void attr_def(FILE* f, const char* name, uint16_t size, uint32_t type) {
+    hstr(f, name);
+    be16(f, size);
+    be32(f, type);
+    for (uint16_t i = 0; i < size; ++i) be32(f, 0);
+  }
+  static void write_bgeo(FILE* f, const std::vector<Particle>& particles) {
+    const uint32_t n = (uint32_t)particles.size();
+    std::fwrite("Bgeo", 1, 4, f);
+    std::fputc('V', f);
+    be32(f, 5);  // version
+    be32(f, n);  // points
+    be32(f, 1);  // primitives: one particle system
+    be32(f, 0);  // point groups
+    be32(f, 0);  // primitive groups
+    be32(f, 3);  // point attributes besides the position: id, velocity, radius
+    be32(f, 0);  // vertex attributes
+    be32(f, 1);  // primitive attributes: generator
+    be32(f, 0);  // detail attributes
+    attr_def(f, "id", 1, 1);
+    attr_def(f, "velocity", 3, 5);
+    attr_def(f, "radius", 1, 0);
+    uint32_t i = 0;
+    for (const Particle& p : particles) {
+      bef(f, p.x[0]);
+      bef(f, p.x[1]);
+      bef(f, p.x[2]);
+      bef(f, 1.0f);
+      be32(f, i++);
+      bef(f, p.v[0]);
+      bef(f, p.v[1]);
+      bef(f, p.v[2]);
+      bef(f, 0.1f);
+    }
+    // primitive attribute dictionary: an indexed string "generator" with the single value "papi"
+    hstr(f, "generator");
+    be16(f, 1);
+    be32(f, 4);
+    be32(f, 1);
+    hstr(f, "papi");
+    // the particle system: key, vertex count, one vertex per point, then its generator index
+    be32(f, 0x00008000u);
+    be32(f, n);
+    for (uint32_t q = 0; q < n; ++q) be32(f, q);
+    be32(f, 0);
+    std::fputc(0x00, f);
+    std::fputc(0xff, f);
   }
 };
 
@@ -157,8 +238,9 @@ class MeshBuilder {
     std::vector<int> F;
     marching_tetrahedra(S, G, V, F);
     for (double& v : V) v *= voxel_dx;
-    if (flags_.laplacian_smooth != 0 || flags_.mesh_face_count != -1)
-      std::cout << "Warning: --laplacian_smooth / --mesh-face-count are not implemented; writing the raw iso-surface" << std::endl;
+    if (flags_.laplacian_smooth != 0 && !smooth_mesh(V, F))  // mesh_builder.h:196-200
+      std::cout << "Warning: the smoothing system is not positive definite (degenerate mesh); smoothing skipped" << std::endl;
+    if (flags_.mesh_face_count != -1) decimate_mesh(V, F, (size_t)std::max(0, flags_.mesh_face_count));  // mesh_builder.h:202-208
     bool ok = true;
     if (!filename.empty()) ok = write_obj(filename, V, F);
     if (V_out) *V_out = std::move(V);

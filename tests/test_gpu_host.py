@@ -106,7 +106,7 @@ def test_cli_rubber_duck_config0(tmp_path):
     scene = os.path.join(ROOT, "scenes", "rubber_duck.toml")
     out = tmp_path / "out"
     r = subprocess.run([cli, "--scene", scene, "--N", "16", "--particle-count", "10000", "--steps", "1000", "--save-dir", str(out),
-                        "--mesh-grid", "32", "--mesh-particle-radius", "2"], capture_output=True, text=True, timeout=600)
+                        "--mesh-grid", "32", "--mesh-particle-radius", "2", "--particle-format", "pda"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     frames = sorted(os.listdir(out / "particles"), key=lambda f: int(f.split("_")[1].split(".")[0]))
     assert len(frames) == 25 and len(os.listdir(out / "meshes")) == 25  # every 41 substeps

@@ -224,6 +224,79 @@ def test_mesh_builder_and_particle_writer(tmp_path):
     assert np.array_equal(data[:, 0], np.arange(len(x))) and np.array_equal(data[:, 1:4].astype(np.float32), x) and (data[:, 7].astype(np.float32) == np.float32(0.1)).all()
 
 
+def test_bgeo_particle_file(tmp_path):
+    """The reference's particle dump format (src/main.cu:109: particles_%d.bgeo through Partio): Houdini
+    classic BGEO v5, big-endian, read back here field by field."""
+    import struct
+
+    s = host.Scene("--scene", os.path.join(SCENES, "rubber_duck.toml"), "-N", "16", "--particle-count", "10000")
+    p = s.active_particles()
+    path = tmp_path / "p.bgeo"
+    s.write_particles(path)
+    b = open(path, "rb").read()
+    assert b[:5] == b"BgeoV"
+    version, npts, nprims, npg, nprg, npa, nva, npra, na = struct.unpack(">9i", b[5:41])
+    assert (version, npts, nprims, npg, nprg, npa, nva, npra, na) == (5, len(p), 1, 0, 0, 3, 0, 1, 0)
+    off = 41
+    names = []
+    for _ in range(3):
+        (ln,) = struct.unpack(">H", b[off:off + 2])
+        name = b[off + 2:off + 2 + ln].decode()
+        size, typ = struct.unpack(">Hi", b[off + 2 + ln:off + 8 + ln])
+        names.append((name, size, typ))
+        off += 8 + ln + 4 * size
+    assert names == [("id", 1, 1), ("velocity", 3, 5), ("radius", 1, 0)]
+    rec = np.frombuffer(b, dtype=np.dtype([("x", ">f4", 4), ("id", ">i4"), ("v", ">f4", 3), ("r", ">f4")]), count=len(p), offset=off)
+    assert np.array_equal(rec["x"][:, :3].astype(np.float32), p["x"]) and (rec["x"][:, 3] == 1).all()
+    assert np.array_equal(rec["id"], np.arange(len(p))) and np.array_equal(rec["v"].astype(np.float32), p["v"])
+    assert (rec["r"].astype(np.float32) == np.float32(0.1)).all()
+    off += rec.nbytes
+    assert b[off:off + 2 + 9] == struct.pack(">H", 9) + b"generator"
+    assert b[-2:] == b"\x00\xff"
+    prim = off + 11 + 2 + 4 + 4 + 2 + 4
+    key, nv = struct.unpack(">Ii", b[prim:prim + 8])
+    assert key == 0x8000 and nv == len(p)
+
+
+def test_mesh_smoothing_and_decimation(tmp_path):
+    """--laplacian_smooth (one implicit cotangent-Laplacian step + the reference's unit-area scaling,
+    mesh_builder.h:213-245) and --mesh-face-count (shortest-edge collapse, mesh_builder.h:202-208)."""
+    common = ["--scene", os.path.join(SCENES, "liquid_bunny.toml"), "--N", "32", "--particle-count", "40000", "--mesh-grid", "40",
+              "--mesh-particle-radius", "2"]
+
+    def load(path):
+        V = np.array([l.split()[1:] for l in open(path) if l.startswith("v ")], np.float64)
+        F = np.array([l.split()[1:] for l in open(path) if l.startswith("f ")], np.int64) - 1
+        return V, F
+
+    def area(V, F):
+        return 0.5 * np.linalg.norm(np.cross(V[F[:, 1]] - V[F[:, 0]], V[F[:, 2]] - V[F[:, 0]]), axis=1).sum()
+
+    host.Scene(*common).compute_mesh(tmp_path / "raw.obj")
+    V0, F0 = load(tmp_path / "raw.obj")
+    _, vol0 = _mesh_checks(V0, F0)
+    # decimation: face count reached, still a closed 2-manifold, volume kept within a few per cent
+    target = len(F0) // 4
+    host.Scene(*common, "--mesh-face-count", str(target)).compute_mesh(tmp_path / "dec.obj")
+    V1, F1 = load(tmp_path / "dec.obj")
+    counts, vol1 = _mesh_checks(V1, F1)
+    assert len(F1) <= target and len(F1) > target - 4 and (counts == 2).all()
+    assert abs(vol1 / vol0 - 1) < 0.05
+    assert len(np.unique(F1)) == len(V1)   # vertices compacted
+    # smoothing: same connectivity, unit area afterwards (the reference divides by sqrt(area)), and before
+    # that normalisation the surface is smoother: the total area of the rescaled mesh shrinks
+    host.Scene(*common, "--laplacian_smooth", "1").compute_mesh(tmp_path / "smooth.obj")
+    V2, F2 = load(tmp_path / "smooth.obj")
+    assert np.array_equal(F2, F0) and abs(area(V2, F2) - 1.0) < 1e-9
+    # undo the normalisation with the raw mesh's scale: centroid-relative sizes compare
+    c0, c2 = V0.mean(0), V2.mean(0)
+    ratio = np.linalg.norm(V2 - c2, axis=1).mean() / np.linalg.norm(V0 - c0, axis=1).mean()
+    V2r = c0 + (V2 - c2) / ratio
+    rough = lambda V: np.linalg.norm(V[F0[:, 0]] + V[F0[:, 1]] + V[F0[:, 2]] - 3 * V[F0[:, 0]], axis=1).std()
+    assert area(V2r, F0) < area(V0, F0)     # mean-curvature flow shrinks area at equal mean radius
+    assert rough(V2r) <= rough(V0) * 1.05
+
+
 def test_toml_subset_edge_cases(tmp_path):
     """Comments, multi-line arrays, literal strings, escapes, underscores and exponents parse like
     tomllib; constructs outside the subset are rejected instead of being misread."""
