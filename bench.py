@@ -240,16 +240,24 @@ class Ctx:
 def make_sim(ctx, model, scaling, particles_per_gpu, svd, sort_every, pipeline="handover", p2g="runs", g2p="tile", rebin_permille=0, ghost=0):
     import mpm_b200
 
-    N, slabs = workload(ctx.world, scaling)
-    xb, xe = slabs[ctx.rank]
-    P_total = particles_per_gpu * (ctx.world if scaling == "weak" else 1)
+    emu = getattr(ctx.args, "emulate_rank", None)
+    if emu:  # experiments: the slab, grid and particle share of rank R of W on ONE GPU, without neighbours
+        r, w = (int(v) for v in emu.split("/"))
+        N, slabs = workload(w, scaling)
+        xb, xe = slabs[r]
+        P_total = particles_per_gpu * (w if scaling == "weak" else 1)
+        slabs = [slabs[r]]
+    else:
+        N, slabs = workload(ctx.world, scaling)
+        xb, xe = slabs[ctx.rank]
+        P_total = particles_per_gpu * (ctx.world if scaling == "weak" else 1)
     density = P_total / 0.512  # --particle-count: the block fills 0.8^3 of the unit cube
     snow = model == "snow"
     if snow:  # scenes/snowman.toml material
         mats = mpm_b200.make_material(1.0 / density, 700.0, 1.4e5, 0.2, 10.0, 0.975, 1.0075)
     else:
         mats = mpm_b200.make_material(1.0 / density, 1000.0, 1.4e5, 0.2, 0.0, 0.0, 1e30)
-    cap = int(P_total / ctx.world * 1.15) if ctx.world > 1 else 0
+    cap = int(P_total / ctx.world * 1.15) if ctx.world > 1 else (int(particles_per_gpu * 1.15) if emu else 0)
     sim = mpm_b200.Sim(N, 1e-4, mats, model=mpm_b200.SNOW if snow else mpm_b200.FIXED_COROTATED,
                        svd_mode=mpm_b200.SVD_FAST if svd == "fast" else mpm_b200.SVD_EXACT, sort_every=sort_every,
                        x_begin=xb, x_end=xe, device=ctx.local_rank, capacity=cap,
@@ -413,6 +421,9 @@ def main():
                     help="material model; snow = BASELINE.json configs[4] (plasticity via svd3 in G2P)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--emulate-rank", default=None, metavar="R/W",
+                    help="experiments on one GPU: the slab geometry (N, planes, particle share) of rank R of W, without neighbours; "
+                         "use with MPM_BENCH_NO_CHECKS=1 --no-extras --no-e2e")
     ap.add_argument("--no-extras", action="store_true", help="skip the extra configurations / stressed workloads / N-rank parity")
     args = ap.parse_args()
     if args.impl == "reference":

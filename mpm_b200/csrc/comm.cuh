@@ -41,8 +41,9 @@ __global__ void __launch_bounds__(256) halo_add_kernel(float4* __restrict__ grid
 // dest 0 = lower neighbour, 1 = upper neighbour.  Packed layout: stream s of destination d at
 // buf + (d * kMigRows + s) * cap; rows NSTREAM / NSTREAM+1 carry id and material as bits.
 constexpr int kMigRows = NSTREAM + 2;
+// keys (optional): the cell keys the P2G of this substep wrote for the re-bin; a leaver's becomes dead_key
 __global__ void __launch_bounds__(256) migrate_pack_kernel(Soa p, size_t count, KParams k, float* __restrict__ buf, size_t cap,
-                                                           unsigned int* __restrict__ counters) {
+                                                           unsigned int* __restrict__ counters, uint32_t* __restrict__ keys, uint32_t dead_key) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
   if (p.id[i] == kDeadId) return;
@@ -64,10 +65,13 @@ __global__ void __launch_bounds__(256) migrate_pack_kernel(Soa p, size_t count, 
     base[(size_t)(NSTREAM + 1) * cap] = __uint_as_float((uint32_t)p.mat[i]);
   }
   p.id[i] = kDeadId;  // tombstone: sorted behind the live particles by the re-bin that follows
+  if (keys) keys[i] = dead_key;
 }
 
-// arrivals from one neighbour (stream-major in `buf`, row stride cap) into slots [first, first + n)
-__global__ void __launch_bounds__(256) migrate_unpack_kernel(Soa p, size_t first, size_t n, const float* __restrict__ buf, size_t cap) {
+// arrivals from one neighbour (stream-major in `buf`, row stride cap) into slots [first, first + n);
+// keys / vals (optional): their entries of the (key, index) pairs the re-bin sorts
+__global__ void __launch_bounds__(256) migrate_unpack_kernel(Soa p, size_t first, size_t n, const float* __restrict__ buf, size_t cap, KParams k,
+                                                             uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float* __restrict__ c = p.col(first + i);
@@ -75,6 +79,18 @@ __global__ void __launch_bounds__(256) migrate_unpack_kernel(Soa p, size_t first
   for (int s = 0; s < NSTREAM; ++s) c[s * kTile] = buf[(size_t)s * cap + i];
   p.id[first + i] = __float_as_uint(buf[(size_t)NSTREAM * cap + i]);
   p.mat[first + i] = (uint8_t)__float_as_uint(buf[(size_t)(NSTREAM + 1) * cap + i]);
+  if (keys) {
+    int b[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      float fx, w[3];
+      bspline(buf[(size_t)(SX + a) * cap + i], k.dx_inv, b[a], fx, w);
+      b[a] = min(max(b[a], 0), k.N - 1);
+    }
+    const int bx = min(max(b[0] - k.x0, 0), k.nxl - 1);
+    keys[first + i] = (uint32_t)((bx * k.N + b[1]) * k.N + b[2]);
+    vals[first + i] = (uint32_t)(first + i);
+  }
 }
 
 struct Comm {
@@ -200,14 +216,14 @@ struct Comm {
   // d_escaped: this rank's count of particle-substeps that scattered outside its planes since the last
   // re-bin; *escaped_all = the sum over ALL ranks, so that every rank takes the same decision about it.
   int migrate(Soa& p, size_t* count, size_t capacity, const KParams& k, cudaStream_t stream, uint64_t* launches, size_t* n_dead,
-              const unsigned int* d_escaped, unsigned int* escaped_all) {
+              const unsigned int* d_escaped, unsigned int* escaped_all, uint32_t* keys = nullptr, uint32_t* vals = nullptr, uint32_t dead_key = 0) {
     *n_dead = 0;
     *escaped_all = 0;
     if (!on) return 0;
     cudaError_t e = cudaMemsetAsync(d_counts, 0, sizeof(unsigned int) * 8, stream);
     if (e != cudaSuccess) return failc("memset(counts)", e);
     if (*count) {
-      migrate_pack_kernel<<<(unsigned)((*count + 255) / 256), 256, 0, stream>>>(p, *count, k, send_buf, mig_cap, d_counts);
+      migrate_pack_kernel<<<(unsigned)((*count + 255) / 256), 256, 0, stream>>>(p, *count, k, send_buf, mig_cap, d_counts, keys, dead_key);
       ++*launches;
     }
     // counts: mine out -> neighbours' in
@@ -258,11 +274,12 @@ struct Comm {
     if (r != ncclSuccess) return fail("ncclGroupEnd(payload)", r);
     if (int rc = check_async()) return rc;
     if (in_lo) {
-      migrate_unpack_kernel<<<(unsigned)((in_lo + 255) / 256), 256, 0, stream>>>(p, first_lo, in_lo, recv_buf, mig_cap);
+      migrate_unpack_kernel<<<(unsigned)((in_lo + 255) / 256), 256, 0, stream>>>(p, first_lo, in_lo, recv_buf, mig_cap, k, keys, vals);
       ++*launches;
     }
     if (in_hi) {
-      migrate_unpack_kernel<<<(unsigned)((in_hi + 255) / 256), 256, 0, stream>>>(p, first_hi, in_hi, recv_buf + (size_t)kMigRows * mig_cap, mig_cap);
+      migrate_unpack_kernel<<<(unsigned)((in_hi + 255) / 256), 256, 0, stream>>>(p, first_hi, in_hi, recv_buf + (size_t)kMigRows * mig_cap, mig_cap, k, keys,
+                                                                                 vals);
       ++*launches;
     }
     e = cudaGetLastError();

@@ -284,8 +284,9 @@ int do_sort(MpmSim* sim, bool partial = false, bool keys_ready = false) {
     // that is a configuration error (ghost width / re-bin cadence too small for the velocities), and
     // every rank must stop for it, not only the one that saw it
     unsigned int escaped = 0;
+    // (with the cell keys P2G wrote for this re-bin: leavers' keys become the tombstone key, arrivals get theirs)
     if (sim->comm.migrate(sim->soa[sim->cur], &sim->count, sim->capacity, sim->k, sim->stream, &sim->launches, &n_dead, &sim->d_diag->escaped,
-                          &escaped))
+                          &escaped, keys_ready ? sim->keys[0] : nullptr, keys_ready ? sim->vals[0] : nullptr, (uint32_t)sim->grid_nodes))
       return fail(sim, "particle migration failed: %s", sim->comm.error());
     CK(cudaMemsetAsync(&sim->d_diag->escaped, 0, sizeof(unsigned int), sim->stream));
     if (escaped)
@@ -770,9 +771,9 @@ int mpm_advance(MpmSim* sim, int n_substeps) {
     if (due) {  // the keys P2G writes come with fresh out-of-domain / non-finite counts
       CK(cudaMemsetAsync(&sim->d_diag->nonfinite, 0, 2 * sizeof(unsigned int), sim->stream));
     }
-    bool keys_ready = false;  // slab handles tombstone leavers at the re-bin, which changes their keys
+    bool keys_ready = false;
     if (int rc = do_reset(sim)) return rc;
-    if (int rc = do_p2g_and_exchange(sim, due && !sim->comm.active(), &keys_ready)) return rc;
+    if (int rc = do_p2g_and_exchange(sim, due, &keys_ready)) return rc;
     if (int rc = do_grid(sim)) return rc;
     // a due re-bin runs here: G2P is about to overwrite v and C, so only x, F, Jp have to move (the
     // keys come from the positions this substep started with).  Slab handles migrate whole particle

@@ -33,6 +33,14 @@ namespace mpm {
 #ifndef MPM_P2G_MINBLK
 #define MPM_P2G_MINBLK 4
 #endif
+#ifndef MPM_STREAM_HINTS
+#define MPM_STREAM_HINTS 1  // particle streams are touched once per kernel: evict-first loads
+#endif
+#if MPM_STREAM_HINTS
+#define MPM_LDP(ptr) __ldcs(ptr)
+#else
+#define MPM_LDP(ptr) (*(ptr))
+#endif
 constexpr int kP2gBlock = kTile;
 constexpr int kRunPosBits = 8;  // run list entry = first particle | (length - 1) << kRunPosBits
 constexpr uint32_t kInvalidKey = 0xffffffffu;
@@ -232,14 +240,14 @@ p2g_sched_kernel(Soa p, size_t count, const MatTable<Material> mats, float4* __r
     float x[3], v[3];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-      x[a] = col[(SX + a) * kTile];
-      v[a] = col[(SV + a) * kTile];
+      x[a] = MPM_LDP(col + (SX + a) * kTile);
+      v[a] = MPM_LDP(col + (SV + a) * kTile);
     }
     Mat A;  // C, or dx * affine when handed over
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
-      for (int c = 0; c < 3; ++c) A.m[r][c] = col[(SC + 3 * r + c) * kTile];
+      for (int c = 0; c < 3; ++c) A.m[r][c] = MPM_LDP(col + (SC + 3 * r + c) * kTile);
     const Material m = mats.template get<ONE_MAT>(p.mat, pi);
     if constexpr (!HANDOVER) {
       Particle part;
@@ -247,10 +255,10 @@ p2g_sched_kernel(Soa p, size_t count, const MatTable<Material> mats, float4* __r
 #pragma unroll
       for (int r = 0; r < 3; ++r)
 #pragma unroll
-        for (int c = 0; c < 3; ++c) part.F.m[r][c] = col[(SF + 3 * r + c) * kTile];
+        for (int c = 0; c < 3; ++c) part.F.m[r][c] = MPM_LDP(col + (SF + 3 * r + c) * kTile);
       part.C = A;
       part.Jp = 1.0f;
-      if (MaterialTraits<Material>::kMutatesJp || diag->jp_not_one) part.Jp = col[SJ * kTile];
+      if (MaterialTraits<Material>::kMutatesJp || diag->jp_not_one) part.Jp = MPM_LDP(col + SJ * kTile);
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
         part.x(a) = x[a];

@@ -73,6 +73,19 @@ __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, u
   }
   __syncwarp();
 }
+// L2 eviction policy for data that is touched once per kernel (the particle streams): evict first, so
+// that it does not push the grid planes out of L2 between the passes that reuse them
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+               : "memory");
+}
 // global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
