@@ -46,28 +46,97 @@ __global__ void aos_overwrite_kernel(const MpmParticle* __restrict__ aos, Soa p,
   if (q.Jp != 1.0f) diag->jp_not_one = 1u;
 }
 
-// writes particle r to aos[id[r] - first_id]: restores upload order
-__global__ void soa_to_aos_kernel(Soa p, size_t count, MpmParticle* __restrict__ aos, uint32_t first_id, bool by_id) {
+// ---- tile-wise conversion through shared memory ----------------------------------------------------
+// A thread that reads or writes "its" 104-byte record touches 26 words 104 bytes apart from its
+// neighbour's: every warp instruction hits 32 sectors for 128 useful bytes.  Here a CTA moves one
+// 256-particle tile: the SoA side is read / written row by row (coalesced), the AoS side record by
+// record with 26 consecutive lanes on the 26 words of one record (contiguous 104 bytes), and the
+// transposition happens in shared memory ([particle][27]: odd stride, no bank conflicts either way).
+constexpr int kRecWords = (int)(sizeof(MpmParticle) / 4);  // 26
+static_assert(sizeof(MpmParticle) == 104, "record layout");
+// word w of the AoS record <-> stream row: word 0 = material_type (+pad), 1..3 x, 4..6 v, 7..15 F (column-major),
+// 16..24 C (column-major), 25 Jp
+__device__ __forceinline__ int aos_word_of_row(int row) {
+  if (row >= SX && row < SX + 3) return 1 + (row - SX);
+  if (row >= SV && row < SV + 3) return 4 + (row - SV);
+  if (row >= SF && row < SF + 9) {
+    const int e = row - SF;  // row-major 3 r + c -> column-major 3 c + r
+    return 7 + 3 * (e % 3) + e / 3;
+  }
+  if (row >= SC && row < SC + 9) {
+    const int e = row - SC;
+    return 16 + 3 * (e % 3) + e / 3;
+  }
+  return 25;  // SJ
+}
+
+// particle r of the tile -> aos[id[r] - first_id] (by_id: restores upload order) or aos[r]
+__global__ void __launch_bounds__(kTile) soa_to_aos_kernel(Soa p, size_t count, MpmParticle* __restrict__ aos, uint32_t first_id, bool by_id) {
+  __shared__ uint32_t rec[kTile * (kRecWords + 1)];
+  __shared__ uint32_t dst[kTile];
+  const int tid = threadIdx.x;
+  const size_t i = (size_t)blockIdx.x * kTile + tid;
+  const size_t n_here = min((size_t)kTile, count - (size_t)blockIdx.x * kTile);
+  if (i < count) {
+    const float* __restrict__ c = p.tile(blockIdx.x) + tid;
+    uint32_t* r = rec + tid * (kRecWords + 1);
+    r[0] = (uint32_t)p.mat[i];  // pad bytes zero
+#pragma unroll
+    for (int row = 0; row < NSTREAM; ++row) r[aos_word_of_row(row)] = __float_as_uint(c[row * kTile]);
+    dst[tid] = by_id ? (p.id[i] - first_id) : (uint32_t)i;
+  }
+  __syncthreads();
+  uint32_t* __restrict__ out = reinterpret_cast<uint32_t*>(aos);
+  for (int e = tid; e < (int)n_here * kRecWords; e += kTile) {
+    const int q = e / kRecWords, w = e - q * kRecWords;
+    out[(size_t)dst[q] * kRecWords + w] = rec[q * (kRecWords + 1) + w];
+  }
+}
+
+// cell keys straight from the uploaded AoS records (the pairs the re-bin sorts), and the Jp != 1 flag
+__global__ void __launch_bounds__(256) aos_keys_kernel(const MpmParticle* __restrict__ aos, size_t count, KParams k, uint32_t* __restrict__ keys,
+                                                       uint32_t* __restrict__ vals, DeviceDiag* __restrict__ diag) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
-  const float* c = p.col(i);
-  MpmParticle q;
-  q.material_type = p.mat[i];
-  q.pad_[0] = q.pad_[1] = q.pad_[2] = 0;
+  const MpmParticle& q = aos[i];
+  int b[3];
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
-    q.x[a] = c[(SX + a) * kTile];
-    q.v[a] = c[(SV + a) * kTile];
+    float fx, w[3];
+    bspline(q.x[a], k.dx_inv, b[a], fx, w);
+    b[a] = min(max(b[a], 0), k.N - 1);
   }
+  const int bx = min(max(b[0] - k.x0, 0), k.nxl - 1);
+  keys[i] = (uint32_t)((bx * k.N + b[1]) * k.N + b[2]);
+  vals[i] = (uint32_t)i;
+  if (q.Jp != 1.0f) diag->jp_not_one = 1u;
+}
+
+// slot r of the (sorted) SoA <- aos[perm[r]]: conversion and cell-order permutation in one pass, so that
+// an upload never moves the particles through the SoA twice; ids: upload order (first_id + index)
+__global__ void __launch_bounds__(kTile) aos_gather_to_soa_kernel(const MpmParticle* __restrict__ aos, const uint32_t* __restrict__ perm, Soa p,
+                                                                  size_t count, uint32_t first_id) {
+  __shared__ uint32_t rec[kTile * (kRecWords + 1)];
+  __shared__ uint32_t src[kTile];
+  const int tid = threadIdx.x;
+  const size_t i = (size_t)blockIdx.x * kTile + tid;
+  const size_t n_here = min((size_t)kTile, count - (size_t)blockIdx.x * kTile);
+  if (i < count) src[tid] = perm[i];
+  __syncthreads();
+  const uint32_t* __restrict__ in = reinterpret_cast<const uint32_t*>(aos);
+  for (int e = tid; e < (int)n_here * kRecWords; e += kTile) {
+    const int q = e / kRecWords, w = e - q * kRecWords;
+    rec[q * (kRecWords + 1) + w] = in[(size_t)src[q] * kRecWords + w];
+  }
+  __syncthreads();
+  if (i < count) {
+    float* __restrict__ c = p.tile(blockIdx.x) + tid;
+    const uint32_t* r = rec + tid * (kRecWords + 1);
 #pragma unroll
-  for (int r = 0; r < 3; ++r)
-#pragma unroll
-    for (int cc = 0; cc < 3; ++cc) {
-      q.F[3 * cc + r] = c[(SF + 3 * r + cc) * kTile];
-      q.C[3 * cc + r] = c[(SC + 3 * r + cc) * kTile];
-    }
-  q.Jp = c[SJ * kTile];
-  aos[by_id ? (size_t)(p.id[i] - first_id) : i] = q;  // slab handles: current (cell-sorted) order
+    for (int row = 0; row < NSTREAM; ++row) c[row * kTile] = __uint_as_float(r[aos_word_of_row(row)]);
+    p.id[i] = first_id + src[tid];
+    p.mat[i] = (uint8_t)(r[0] & 0xffu);
+  }
 }
 
 __global__ void positions_kernel(Soa p, size_t count, float* __restrict__ xyz, uint32_t first_id, bool by_id) {

@@ -270,6 +270,18 @@ void radix_pass(MpmSim* sim, int in, size_t n, int shift, int n_tiles) {
   sim->launches += 5;
 }
 
+// stable LSD radix sort of the (key, index) pairs in keys[0] / vals[0]; returns the buffer that holds the result
+int sort_pairs(MpmSim* sim, size_t n) {
+  const int n_tiles = (int)((n + kSortTile - 1) / kSortTile);
+  const int bits = radix_bits(sim->key_bits);
+  int in = 0;
+  for (int shift = 0; shift < sim->key_bits; shift += bits) {
+    if (bits == 8) radix_pass<8>(sim, in, n, shift, n_tiles); else radix_pass<9>(sim, in, n, shift, n_tiles);
+    in ^= 1;
+  }
+  return in;
+}
+
 // partial: called between the grid update and G2P, permutes only what G2P reads (sort.cuh)
 int do_sort(MpmSim* sim, bool partial = false, bool keys_ready = false) {
   StageTimer tm(sim, MPM_STAGE_SORT);
@@ -297,18 +309,11 @@ int do_sort(MpmSim* sim, bool partial = false, bool keys_ready = false) {
   if (n == 0) return 0;
   Soa& src = sim->soa[sim->cur];
   const uint32_t dead_key = (uint32_t)sim->grid_nodes;  // behind every live key
-  const int sort_bits = sim->key_bits;
   if (!keys_ready) {  // else the P2G of this substep wrote them (p2g_sched.cuh)
     cell_key_kernel<<<blocks_for(n, 256), 256, 0, sim->stream>>>(src, n, sim->k, sim->keys[0], sim->vals[0], dead_key);
     sim->launches++;
   }
-  const int n_tiles = (int)((n + kSortTile - 1) / kSortTile);
-  const int bits = radix_bits(sort_bits);
-  int in = 0;
-  for (int shift = 0; shift < sort_bits; shift += bits) {
-    if (bits == 8) radix_pass<8>(sim, in, n, shift, n_tiles); else radix_pass<9>(sim, in, n, shift, n_tiles);
-    in ^= 1;
-  }
+  const int in = sort_pairs(sim, n);
   sim->sorted_cur = in;
   Soa& dst = sim->soa[sim->cur ^ 1];
   if (partial) permute_kernel<true><<<blocks_for(n, 256), 256, 0, sim->stream>>>(src, dst, sim->vals[in], n, sim->k);
@@ -625,8 +630,25 @@ static int upload_impl(MpmSim* sim, const MpmParticle* particles, size_t count, 
   sim->cur = 0;
   sim->form_ad = false;
   CK(cudaMemsetAsync(&sim->d_diag->jp_not_one, 0, sizeof(unsigned int), sim->stream));
+  if (count) CK(cudaMemcpyAsync(sim->aos_stage, particles, sizeof(MpmParticle) * count, cudaMemcpyHostToDevice, sim->stream));
+  if (count && !sim->comm.active() && !ids) {
+    // the common path: keys from the records, sort the (key, index) pairs, then ONE pass that gathers the
+    // records in cell order and writes the SoA — the particles never travel through the SoA unsorted
+    StageTimer tm(sim, MPM_STAGE_SORT);
+    sim->steps_since_sort = 0;
+    sim->rebins++;
+    sim->moved_seen = 0;
+    sim->moved_pending = false;
+    CK(cudaMemsetAsync(sim->d_moved, 0, sizeof(unsigned long long), sim->stream));
+    aos_keys_kernel<<<blocks_for(count, 256), 256, 0, sim->stream>>>(sim->aos_stage, count, sim->k, sim->keys[0], sim->vals[0], sim->d_diag);
+    const int in = sort_pairs(sim, count);
+    sim->sorted_cur = in;
+    aos_gather_to_soa_kernel<<<blocks_for(count, kTile), kTile, 0, sim->stream>>>(sim->aos_stage, sim->vals[in], sim->soa[0], count, 0);
+    sim->launches += 2;
+    CK(cudaGetLastError());
+    return 0;
+  }
   if (count) {
-    CK(cudaMemcpyAsync(sim->aos_stage, particles, sizeof(MpmParticle) * count, cudaMemcpyHostToDevice, sim->stream));
     aos_to_soa_kernel<<<blocks_for(count, 256), 256, 0, sim->stream>>>(sim->aos_stage, sim->soa[0], count, 0, 0, sim->d_diag);
     sim->launches++;
     CK(cudaGetLastError());
@@ -669,7 +691,7 @@ int mpm_download_particles_aos(MpmSim* sim, MpmParticle* particles, size_t capac
   if (capacity < sim->count) return fail(sim, "mpm_download_particles_aos: capacity %zu < %zu", capacity, sim->count);
   if (sim->count == 0) return 0;
   if (int rc = ensure_stage(sim, sim->count)) return rc;
-  soa_to_aos_kernel<<<blocks_for(sim->count, 256), 256, 0, sim->stream>>>(sim->soa[sim->cur], sim->count, sim->aos_stage, sim->first_id, sim->whole_domain);
+  soa_to_aos_kernel<<<blocks_for(sim->count, kTile), kTile, 0, sim->stream>>>(sim->soa[sim->cur], sim->count, sim->aos_stage, sim->first_id, sim->whole_domain);
   sim->launches++;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(particles, sim->aos_stage, sizeof(MpmParticle) * sim->count, cudaMemcpyDeviceToHost, sim->stream));

@@ -17,6 +17,8 @@ import scenes  # noqa: E402
 
 N, DT, STEPS = 32, 1e-4, 40
 p, mats = scenes.two_spheres(N, kind=ol.JELLY)
+p["Jp"][:100] = 0.5     # outside the clamp of the end-of-step hook (0.6 .. 20): the hook must pull them in
+p["Jp"][100:200] = 25.0
 raw = np.ascontiguousarray(mats[:5], np.float32).tobytes()  # UserHardeningSolid: volume, mass, mu0, lambda0, hardening
 out = {"staged_flag": {}}
 for model in (16, 17):

@@ -29,7 +29,7 @@ def test_user_defined_material_against_checker():
         assert e["p2g"] < 1e-5, (model, e)        # atomics reorder sums
         assert e["g2p_F"] < 1e-5 and e["g2p_Jp"] < 1e-5, (model, e)
         assert e["x"] < 1e-3 and e["v"] < 5e-2, (model, e)
-        assert e["Jp_changed"] > 1e-4               # the mutation hook ran in the checker, and the states still agree
+        assert e["Jp_changed"] > 0.09               # the end-of-step hook clamped the out-of-range Jp, in the checker and (g2p_Jp) here
 
 
 def test_default_library_has_no_user_models():
