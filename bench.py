@@ -237,6 +237,38 @@ class Ctx:
         sys.exit(3)
 
 
+class numa_local:
+    """Runs its body on the CPUs closest to this rank's GPU (NVML's affinity mask), so that the pinned
+    host buffer allocated inside is placed on that NUMA node: 8 ranks x 2 x 7 GB per frame otherwise
+    cross the socket interconnect.  No-op when NVML is not available."""
+
+    def __init__(self, device_index):
+        self.device_index = device_index
+        self.saved = None
+
+    def __enter__(self):
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.device_index)
+            n_cpus = os.cpu_count() or 1
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpus + 63) // 64)
+            cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+            allowed = os.sched_getaffinity(0)
+            if cpus & allowed:
+                self.saved = allowed
+                os.sched_setaffinity(0, cpus & allowed)
+        except Exception:
+            self.saved = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.saved is not None:
+            os.sched_setaffinity(0, self.saved)
+        return False
+
+
 def make_sim(ctx, model, scaling, particles_per_gpu, svd, sort_every, pipeline="handover", p2g="runs", g2p="tile", rebin_permille=0, ghost=0):
     import mpm_b200
 
@@ -371,6 +403,40 @@ def parity_nranks(ctx):
     return out
 
 
+def small_scenes():
+    """BASELINE.json configs[0..2] (the reference's README command lines, stand-in meshes) through the
+    host facade: ms per substep, with the launches replayed as CUDA graphs (default for small scenes)
+    and without.  These scenes are launch-bound, not bandwidth-bound."""
+    from mpm_b200 import host
+
+    out = {}
+    cwd = os.getcwd()
+    os.chdir(ROOT)
+    try:
+        for name, line in (("config0_rubber_duck", "--scene scenes/rubber_duck.toml -N 16 --particle-count 10000"),
+                           ("config1_snowman", "--scene scenes/snowman.toml -N 64 --particle-count 500000"),
+                           ("config2_liquid_bunny", "--scene scenes/liquid_bunny.toml -N 32 --particle-count 1000000")):
+            rec = {"command": line}
+            for graphs in ("auto", "off"):
+                s = host.Scene(*line.split(), "--graphs", graphs, "--svd", "fast")
+                n = len(s.active_particles())
+                s.init_cuda()
+                s.advance(200)
+                s.sync_device()
+                steps = 2000
+                t0 = time.perf_counter()
+                s.advance(steps)
+                s.sync_device()   # includes one download of the particles, like the reference's loop every 20 substeps
+                dt = time.perf_counter() - t0
+                rec["particles"] = n
+                rec["ms_per_substep_graphs_" + graphs] = 1e3 * dt / steps
+                s.close()
+            out[name] = rec
+    finally:
+        os.chdir(cwd)
+    return out
+
+
 def invariants(ctx, sim, P_total, mass, slab, N):
     """Size-independent self-checks on the benchmark state (outside every timed region)."""
     P_all = ctx.reduce([float(sim.count)])[0]
@@ -491,7 +557,9 @@ def main():
     e2e = None
     if not args.no_e2e:
         n_host = P_local
-        host = torch.empty(n_host * 104, dtype=torch.uint8, pin_memory=True)
+        with numa_local(ctx.local_rank):
+            host = torch.empty(n_host * 104, dtype=torch.uint8, pin_memory=True)
+            host.zero_()
         got = sim.download_ptr(host.data_ptr(), n_host)  # current state as the host-side truth
         assert got == n_host
         ctx.barrier()
@@ -529,6 +597,7 @@ def main():
         }
         if world == 1:
             stressed["snow_exact_svd"] = short_leg(ctx, "snow", args.scaling, "exact", 8)
+    small = small_scenes() if (full and world == 1) else None
 
     if rank == 0:
         snow = args.model == "snow"
@@ -552,6 +621,8 @@ def main():
             out["configs"] = configs
         if stressed is not None:
             out["stressed"] = stressed
+        if small is not None:
+            out["small_scenes"] = small
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline()
         print(json.dumps(out))

@@ -47,6 +47,11 @@ enum { MPM_G2P_TILE = 0, MPM_G2P_DIRECT = 1 };
  * boundary.  Same arithmetic per particle either way.  CLASSIC: every P2G evaluates the material
  * itself, as the reference does (also what DIRECT kernels and single-substep calls get). */
 enum { MPM_PIPE_HANDOVER = 0, MPM_PIPE_CLASSIC = 1 };
+/* CUDA graphs.  A small scene is launch-bound (a substep is 4 launches of a few microseconds each): the
+ * launches of one mpm_advance(n) call are captured once per (n, phase of the re-bin cadence, buffer parity)
+ * and replayed afterwards.  AUTO: when the handle holds at most 4 M particles; never with rebin_permille,
+ * on slab handles or while stage timing is on (those take decisions on the host between the launches). */
+enum { MPM_GRAPH_AUTO = 0, MPM_GRAPH_OFF = 1, MPM_GRAPH_ON = 2 };
 /* stage indices for mpm_get_stage_times */
 enum { MPM_STAGE_SORT = 0, MPM_STAGE_RESET = 1, MPM_STAGE_P2G = 2, MPM_STAGE_GRID = 3, MPM_STAGE_G2P = 4,
        MPM_STAGE_EXCHANGE = 5, MPM_STAGE_COUNT = 6 };
@@ -94,7 +99,7 @@ typedef struct MpmParams {
                            G2P_TILE, a single-device handle — slab handles keep the fixed
                            cadence, their ranks must re-bin in the same substep); sort_every = 0 then means
                            "only on demand" */
-  uint32_t reserved_;   /* must be 0 */
+  uint32_t graph_mode;  /* MPM_GRAPH_*: replay mpm_advance calls as CUDA graphs */
 } MpmParams;
 
 typedef struct MpmSim MpmSim;
@@ -152,6 +157,7 @@ double mpm_time(const MpmSim* sim);           /* Simulation::t */
 uint64_t mpm_substeps_done(const MpmSim* sim);
 uint64_t mpm_kernel_launches(const MpmSim* sim); /* kernels this handle has launched so far */
 uint64_t mpm_rebins_done(const MpmSim* sim);     /* re-bins (sort + permute) so far, the one at upload included */
+uint64_t mpm_graph_replays(const MpmSim* sim);   /* mpm_advance calls served by replaying a captured CUDA graph */
 
 /* single stages, for parity tests and profiling (same kernels mpm_advance runs) */
 int mpm_stage_sort(MpmSim* sim);        /* north-star stage (1): cell keys, radix sort, SoA permute */

@@ -11,6 +11,7 @@ SVD_EXACT, SVD_FAST = 0, 1
 P2G_RUNS, P2G_DIRECT = 0, 1
 G2P_TILE, G2P_DIRECT = 0, 1
 PIPE_HANDOVER, PIPE_CLASSIC = 0, 1
+GRAPH_AUTO, GRAPH_OFF, GRAPH_ON = 0, 1, 2
 STAGES = ("sort", "reset", "p2g", "grid", "g2p", "exchange")
 
 # MpmParticle == the reference's MLS_APIC_Particle (104 bytes, matrices column-major)
@@ -28,7 +29,7 @@ class MpmParams(ctypes.Structure):
                 ("x_end", ctypes.c_uint32), ("device", ctypes.c_int32), ("capacity", ctypes.c_uint64),
                 ("p2g_mode", ctypes.c_uint32), ("ghost", ctypes.c_uint32), ("g2p_mode", ctypes.c_uint32),
                 ("pipeline", ctypes.c_uint32), ("rebin_permille", ctypes.c_uint32),
-                ("reserved_", ctypes.c_uint32)]
+                ("graph_mode", ctypes.c_uint32)]
 
 
 class MpmError(RuntimeError):
@@ -60,6 +61,8 @@ def lib():
         L.mpm_kernel_launches.argtypes = [_vp]
         L.mpm_rebins_done.restype = ctypes.c_uint64
         L.mpm_rebins_done.argtypes = [_vp]
+        L.mpm_graph_replays.restype = ctypes.c_uint64
+        L.mpm_graph_replays.argtypes = [_vp]
         L.mpm_stream.restype = _vp
         L.mpm_stream.argtypes = [_vp]
         L.mpm_destroy.restype = None
@@ -116,12 +119,12 @@ class Sim:
 
     def __init__(self, N, dt, materials, model=SNOW, svd_mode=SVD_EXACT, sort_every=0, x_begin=0, x_end=0,
                  device=-1, capacity=0, p2g_mode=P2G_RUNS, ghost=0, g2p_mode=G2P_TILE, pipeline=PIPE_HANDOVER, rebin_permille=0,
-                 raw_materials=None):
+                 raw_materials=None, graph_mode=0):
         """materials: n x 7 floats (MpmMaterial = MMSnow's fields; the leading fields are used by the
         other shipped models).  raw_materials: bytes of n objects of a registered model's own
         material type instead (mpm_create_raw, user-defined materials)."""
         self._h = _vp()
-        self.params = MpmParams(dt, N, model, svd_mode, sort_every, x_begin, x_end, device, capacity, p2g_mode, ghost, g2p_mode, pipeline, rebin_permille, 0)
+        self.params = MpmParams(dt, N, model, svd_mode, sort_every, x_begin, x_end, device, capacity, p2g_mode, ghost, g2p_mode, pipeline, rebin_permille, graph_mode)
         if raw_materials is not None:
             raw, n = raw_materials
             buf = ctypes.create_string_buffer(bytes(raw), len(raw))
@@ -219,6 +222,10 @@ class Sim:
     @property
     def rebins(self):
         return lib().mpm_rebins_done(self._h)
+
+    @property
+    def graph_replays(self):
+        return lib().mpm_graph_replays(self._h)
 
     @property
     def stream(self):

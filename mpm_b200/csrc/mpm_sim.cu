@@ -13,6 +13,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "../../include/mpm_b200.h"
 #include "comm.cuh"
@@ -133,6 +134,20 @@ struct MpmSim {
   uint32_t* h_split = nullptr;  // pinned
   cudaEvent_t split_ev = nullptr;
   bool split_pending = false, split_valid = false;
+
+  // CUDA graphs of whole mpm_advance calls (MpmParams.graph_mode), keyed by everything the launch
+  // sequence depends on; dropped whenever anything but mpm_advance touches the handle
+  struct GraphEntry {
+    int n_substeps, cur, sorted_cur, tile_parity;
+    uint64_t steps_since_sort;
+    size_t count;
+    cudaGraphExec_t exec;
+    // host state after the call
+    int cur_after, sorted_cur_after, tile_parity_after;
+    uint64_t steps_since_sort_after, rebins_delta, launches_delta;
+  };
+  std::vector<GraphEntry> graphs;
+  uint64_t graph_replays = 0;
 
   Comm comm;
   std::string err;
@@ -444,6 +459,11 @@ int bits_for(size_t n) {
 
 }  // namespace
 
+static void drop_graphs(MpmSim* sim) {
+  for (auto& g : sim->graphs) cudaGraphExecDestroy(g.exec);
+  sim->graphs.clear();
+}
+
 extern "C" {
 
 int mpm_abi_version(void) { return MPM_B200_ABI_VERSION; }
@@ -468,7 +488,7 @@ int mpm_create_raw(const MpmParams* params, const void* materials, size_t materi
   if (params->N < 4) return fail(nullptr, "mpm_create: N must be >= 4");
   if (n_materials < 1 || n_materials > 256 || !materials) return fail(nullptr, "mpm_create: need 1..256 materials");
   if (params->svd_mode > MPM_SVD_FAST || params->p2g_mode > MPM_P2G_DIRECT || params->g2p_mode > MPM_G2P_DIRECT ||
-      params->pipeline > MPM_PIPE_CLASSIC || params->rebin_permille > 1000 || params->reserved_ != 0)
+      params->pipeline > MPM_PIPE_CLASSIC || params->rebin_permille > 1000 || params->graph_mode > MPM_GRAPH_ON)
     return fail(nullptr, "mpm_create: bad svd_mode / p2g_mode / g2p_mode / pipeline");
   const ModelOps* ops = find_model(params->model, params->svd_mode);
   if (!ops) return fail(nullptr, "mpm_create: no material model registered under id %u", params->model);
@@ -587,6 +607,7 @@ void mpm_destroy(MpmSim* sim) {
   cudaSetDevice(sim->device);
   if (sim->stream) cudaStreamSynchronize(sim->stream);
   if (sim->comm_stream) cudaStreamSynchronize(sim->comm_stream);
+  drop_graphs(sim);
   sim->comm.destroy();
   for (int b = 0; b < 2; ++b) {
     free_soa(sim->soa[b]);
@@ -622,6 +643,7 @@ const char* mpm_last_error(const MpmSim* sim) { return sim ? sim->err.c_str() : 
 
 static int upload_impl(MpmSim* sim, const MpmParticle* particles, size_t count, const uint32_t* ids) {
   if (!sim || (!particles && count)) return fail(sim, "mpm_upload_particles_aos: null argument");
+  drop_graphs(sim);
   CK(cudaSetDevice(sim->device));
   if (int rc = ensure_capacity(sim, std::max<size_t>(count, 1))) return rc;
   if (int rc = ensure_stage(sim, std::max<size_t>(count, 1))) return rc;
@@ -668,6 +690,7 @@ int mpm_upload_particles_with_ids(MpmSim* sim, const MpmParticle* particles, con
 
 int mpm_append_particles_aos(MpmSim* sim, const MpmParticle* particles, size_t count) {
   if (!sim || (!particles && count)) return fail(sim, "mpm_append_particles_aos: null argument");
+  drop_graphs(sim);
   CK(cudaSetDevice(sim->device));
   if (!sim->whole_domain) return fail(sim, "mpm_append_particles_aos: not for slab handles");
   if (count == 0) return 0;
@@ -722,6 +745,7 @@ int mpm_download_positions(MpmSim* sim, float* xyz, size_t capacity, size_t* cou
 int mpm_generate_dense_block_stressed(MpmSim* sim, uint64_t first_id, uint64_t count, uint32_t seed, float lo, float hi, uint8_t material,
                                       float shear, float f_noise) {
   if (!sim) return 1;
+  drop_graphs(sim);
   CK(cudaSetDevice(sim->device));
   const bool whole = sim->whole_domain;
   if (whole) {
@@ -761,19 +785,18 @@ double mpm_time(const MpmSim* sim) { return sim ? sim->t : 0.0; }
 uint64_t mpm_substeps_done(const MpmSim* sim) { return sim ? sim->substeps : 0; }
 uint64_t mpm_kernel_launches(const MpmSim* sim) { return sim ? sim->launches : 0; }
 uint64_t mpm_rebins_done(const MpmSim* sim) { return sim ? sim->rebins : 0; }
+uint64_t mpm_graph_replays(const MpmSim* sim) { return sim ? sim->graph_replays : 0; }
 void* mpm_stream(MpmSim* sim) { return sim ? (void*)sim->stream : nullptr; }
 
 // single stages, for parity tests and profiling: the same kernels mpm_advance runs, on particles in
 // the reference's form (C, not the handed-over affine matrix)
-int mpm_stage_sort(MpmSim* sim) { if (!sim) return 1; CK(cudaSetDevice(sim->device)); return do_sort(sim); }
+int mpm_stage_sort(MpmSim* sim) { if (!sim) return 1; drop_graphs(sim); CK(cudaSetDevice(sim->device)); return do_sort(sim); }
 int mpm_stage_reset_grid(MpmSim* sim) { if (!sim) return 1; CK(cudaSetDevice(sim->device)); return do_reset(sim); }
 int mpm_stage_p2g(MpmSim* sim) { if (!sim) return 1; CK(cudaSetDevice(sim->device)); return do_p2g_and_exchange(sim, false, nullptr); }
 int mpm_stage_grid_update(MpmSim* sim) { if (!sim) return 1; CK(cudaSetDevice(sim->device)); return do_grid(sim); }
-int mpm_stage_g2p(MpmSim* sim) { if (!sim) return 1; CK(cudaSetDevice(sim->device)); return do_g2p(sim, false); }
+int mpm_stage_g2p(MpmSim* sim) { if (!sim) return 1; drop_graphs(sim); CK(cudaSetDevice(sim->device)); return do_g2p(sim, false); }
 
-int mpm_advance(MpmSim* sim, int n_substeps) {
-  if (!sim) return 1;
-  CK(cudaSetDevice(sim->device));
+static int advance_impl(MpmSim* sim, int n_substeps) {
   for (int s = 0; s < n_substeps; ++s) {
     bool due = sim->par.sort_every && sim->steps_since_sort >= sim->par.sort_every;
     // (not for slab handles: every rank must reach the migration of a re-bin in the same substep)
@@ -818,6 +841,77 @@ int mpm_advance(MpmSim* sim, int n_substeps) {
   return 0;
 }
 
+int mpm_advance(MpmSim* sim, int n_substeps) {
+  if (!sim) return 1;
+  CK(cudaSetDevice(sim->device));
+  if (n_substeps <= 0) return 0;
+  const bool want = sim->par.graph_mode == MPM_GRAPH_ON || (sim->par.graph_mode == MPM_GRAPH_AUTO && sim->count <= (size_t)4 << 20);
+  const bool graphable = want && sim->count > 0 && n_substeps <= 256 && !sim->par.rebin_permille && !sim->comm.active() && !sim->timing;
+  if (!graphable) return advance_impl(sim, n_substeps);
+  for (auto& g : sim->graphs) {
+    if (g.n_substeps == n_substeps && g.cur == sim->cur && g.sorted_cur == sim->sorted_cur && g.tile_parity == sim->tile_parity &&
+        g.steps_since_sort == sim->steps_since_sort && g.count == sim->count) {
+      CK(cudaGraphLaunch(g.exec, sim->stream));
+      sim->cur = g.cur_after;
+      sim->sorted_cur = g.sorted_cur_after;
+      sim->tile_parity = g.tile_parity_after;
+      sim->steps_since_sort = g.steps_since_sort_after;
+      sim->rebins += g.rebins_delta;
+      sim->launches += g.launches_delta;
+      sim->substeps += (uint64_t)n_substeps;
+      for (int s = 0; s < n_substeps; ++s) sim->t += (double)sim->par.dt;  // the same sum as the loop
+      sim->graph_replays++;
+      return 0;
+    }
+  }
+  // first call in this state: capture the launches of the ordinary code path, then run the graph
+  MpmSim::GraphEntry e{};
+  e.n_substeps = n_substeps;
+  e.cur = sim->cur;
+  e.sorted_cur = sim->sorted_cur;
+  e.tile_parity = sim->tile_parity;
+  e.steps_since_sort = sim->steps_since_sort;
+  e.count = sim->count;
+  const uint64_t rebins0 = sim->rebins, launches0 = sim->launches, substeps0 = sim->substeps;
+  const double t0 = sim->t;
+  CK(cudaStreamBeginCapture(sim->stream, cudaStreamCaptureModeThreadLocal));
+  const int rc = advance_impl(sim, n_substeps);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(sim->stream, &graph);
+  cudaGraphExec_t exec = nullptr;
+  if (rc == 0 && ce == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+    cudaGraphDestroy(graph);
+    e.exec = exec;
+    e.cur_after = sim->cur;
+    e.sorted_cur_after = sim->sorted_cur;
+    e.tile_parity_after = sim->tile_parity;
+    e.steps_since_sort_after = sim->steps_since_sort;
+    e.rebins_delta = sim->rebins - rebins0;
+    e.launches_delta = sim->launches - launches0;
+    if (sim->graphs.size() >= 32) {
+      cudaGraphExecDestroy(sim->graphs.front().exec);
+      sim->graphs.erase(sim->graphs.begin());
+    }
+    sim->graphs.push_back(e);
+    CK(cudaGraphLaunch(exec, sim->stream));
+    return 0;
+  }
+  // capture failed: nothing was enqueued; restore the host state and take the ordinary path
+  if (graph) cudaGraphDestroy(graph);
+  cudaGetLastError();
+  sim->cur = e.cur;
+  sim->sorted_cur = e.sorted_cur;
+  sim->tile_parity = e.tile_parity;
+  sim->steps_since_sort = e.steps_since_sort;
+  sim->rebins = rebins0;
+  sim->launches = launches0;
+  sim->substeps = substeps0;
+  sim->t = t0;
+  sim->form_ad = false;
+  sim->par.graph_mode = MPM_GRAPH_OFF;
+  return advance_impl(sim, n_substeps);
+}
+
 int mpm_sync(MpmSim* sim) {
   if (!sim) return 1;
   CK(cudaSetDevice(sim->device));
@@ -845,6 +939,7 @@ int mpm_debug_overwrite_particles_aos(MpmSim* sim, const MpmParticle* particles,
   if (!sim || !particles) return 1;
   CK(cudaSetDevice(sim->device));
   if (count != sim->count || !sim->whole_domain) return fail(sim, "overwrite needs the same particle count on a whole-domain handle");
+  drop_graphs(sim);
   if (count == 0) return 0;
   if (int rc = ensure_stage(sim, count)) return rc;
   CK(cudaMemcpyAsync(sim->aos_stage, particles, sizeof(MpmParticle) * count, cudaMemcpyHostToDevice, sim->stream));

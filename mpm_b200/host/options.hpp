@@ -6,7 +6,7 @@
 // A parse error prints a message and exits with status 1, like the reference (options.h:48-51).  Extensions (not in the reference, all optional):
 // --steps (stop after this many substeps; the reference loops until killed), --svd exact|fast,
 // --model snow|fixed_corotated|jelly (the compile-time MaterialModel alias of include/mpm.cuh:25 as data),
-// --sort-every, --rebin-permille, --sync-every, --frame-rate.
+// --sort-every, --rebin-permille, --sync-every, --frame-rate, --graphs auto|off|on, --particle-format bgeo|pda.
 #pragma once
 #include <cstdint>
 #include <cstdlib>
@@ -43,6 +43,7 @@ struct CLIOptions {
   u32 rebin_permille = 0;  // MpmParams.rebin_permille
   u32 sync_every = 20;  // src/main.cu:99
   u32 frame_rate = 240; // src/main.cu:8
+  std::string graphs = "auto";  // MpmParams.graph_mode: auto | off | on
   std::string particle_format = "bgeo";  // bgeo (the reference, src/main.cu:109) or pda (Partio ASCII)
 
   CLIOptions() { derive(); }
@@ -114,6 +115,7 @@ struct CLIOptions {
         else if (k == "sync-every") sync_every = to_u32(v);
         else if (k == "frame-rate") frame_rate = to_u32(v);
         else if (k == "particle-format") particle_format = v;
+        else if (k == "graphs") graphs = v;
         else {
           err = "Option '" + k + "' does not exist";
           return false;
@@ -123,7 +125,7 @@ struct CLIOptions {
       err = "Argument could not be parsed";
       return false;
     }
-    if (N == 0 || sync_every == 0 || (particle_format != "bgeo" && particle_format != "pda") || (svd != "exact" && svd != "fast") || (model != "snow" && model != "fixed_corotated" && model != "jelly")) {
+    if (N == 0 || sync_every == 0 || (graphs != "auto" && graphs != "off" && graphs != "on") || (particle_format != "bgeo" && particle_format != "pda") || (svd != "exact" && svd != "fast") || (model != "snow" && model != "fixed_corotated" && model != "jelly")) {
       err = "Argument out of range";
       return false;
     }

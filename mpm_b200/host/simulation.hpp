@@ -131,6 +131,7 @@ class Simulation {
     p.svd_mode = opts_.svd == "fast" ? MPM_SVD_FAST : MPM_SVD_EXACT;
     p.sort_every = opts_.sort_every;
     p.rebin_permille = opts_.rebin_permille;
+    p.graph_mode = opts_.graphs == "off" ? MPM_GRAPH_OFF : opts_.graphs == "on" ? MPM_GRAPH_ON : MPM_GRAPH_AUTO;
     p.device = -1;
     p.capacity = std::max<size_t>(getFullParticleCount(), 1);  // every object fits: activation never reallocates
     if (material_models.empty()) throw std::runtime_error("no materials");

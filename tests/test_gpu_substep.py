@@ -344,3 +344,37 @@ def test_free_fall_velocity():
     got = sim.download()
     assert np.allclose(got["v"][:, 1], -9.81 * 50 * DT, rtol=2e-3)
     assert np.abs(got["v"][:, [0, 2]]).max() < 1e-3
+
+
+def test_cuda_graph_replay_of_advance_calls():
+    """MpmParams.graph_mode: the launches of mpm_advance(n) are captured once per state of the re-bin
+    cadence and replayed; the result is the ordinary one (against the checker), interleaved API calls
+    drop the graphs, and the replays are counted."""
+    import mpm_b200
+
+    N, steps = 32, 192
+    p, mats = scenes.two_spheres(N, kind=ol.SNOW, perturb=False)
+    ref, _ = ol.advance(p.copy(), mats, DT, N, ol.SNOW, steps)
+    out = {}
+    for mode in (mpm_b200.GRAPH_ON, mpm_b200.GRAPH_OFF):
+        sim = _sim(N, mats, ol.SNOW, 0, sort_every=8, graph_mode=mode)
+        sim.upload(p)
+        for _ in range(steps // 12):   # 12 substeps per call against a cadence of 8: a handful of (phase, buffer parity) states recur
+            sim.advance(12)
+        out[mode] = (sim.download(), sim.graph_replays, sim.rebins, sim.launches)
+        sim.close()
+    on, off = out[mpm_b200.GRAPH_ON], out[mpm_b200.GRAPH_OFF]
+    assert on[1] >= steps // 24 and off[1] == 0                # every state seen before is a replay
+    assert on[2] == off[2] and on[3] == off[3]                 # same re-bins and launches accounted
+    for got in (on[0], off[0]):
+        assert np.abs(got["x"].astype(np.float64) - ref["x"]).max() * N < 3e-3   # 192 substeps of the impact
+    # an upload in between drops the graphs; the handle keeps working
+    sim = _sim(N, mats, ol.SNOW, 0, sort_every=8, graph_mode=mpm_b200.GRAPH_ON)
+    sim.upload(p)
+    sim.advance(8)
+    sim.advance(8)
+    sim.upload(p)
+    sim.advance(8)
+    got = sim.download()
+    ref8, _ = ol.advance(p.copy(), mats, DT, N, ol.SNOW, 8)
+    assert np.abs(got["x"].astype(np.float64) - ref8["x"]).max() * N < 1e-4
