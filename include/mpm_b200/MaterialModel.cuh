@@ -132,11 +132,23 @@ class MMSnow : public MMFixedCorotated<Particle, Ops> {
   // elastic range: there the reference only re-synthesises F = U S V^T and Jp * det F / det F from the
   // SVD's own round-off (~1e-6), so leaving F and Jp untouched is within the FAST tolerance.
   __device__ __forceinline__ void endOfStepMutation(Particle& particle) const {
+    Mat R;
+    (void)endOfStepMutationR(particle, R);
+  }
+
+  // ---- optional hooks of the hand-over pipeline (mpm_b200/csrc/g2p_tile.cuh) ----
+  // The same mutation, also returning the polar rotation of the MUTATED F when the SVD ran: with
+  // F' = U clamp(S) V^T and clamp(S) > 0 that rotation is U V^T, so the stress of the next substep
+  // (computePF_R) needs no second SVD.  The reference runs svd3 again on F' in its next P2G and gets
+  // the same rotation up to svd3's own accuracy (~1e-6); a handle created with MPM_PIPE_CLASSIC keeps
+  // the reference's two decompositions per particle-step.  Returns false when no SVD ran (FastOps,
+  // particle inside the elastic range): R is then undefined.
+  __device__ __forceinline__ bool endOfStepMutationR(Particle& particle, Mat& R) const {
     Mat& F = particle.F;
     if constexpr (!Ops::kExact) {
       if (mpm::within_elastic_range(F, plast_clamp_lower, plast_clamp_higher)) {
         particle.Jp = clamp(particle.Jp, 0.6f, 20.0f);  // the outer clamp of the Jp update still applies
-        return;
+        return false;
       }
     }
     Mat U, V;
@@ -153,6 +165,14 @@ class MMSnow : public MMFixedCorotated<Particle, Ops> {
     F = mul_abt(US, V);
     const real Fdet = linalg::determinant(F);
     particle.Jp = clamp(particle.Jp * oldJ / Fdet, 0.6f, 20.0f);
+    R = mul_abt(U, V);
+    return sig[2] > 0.0f;  // (a clamp floor <= 0 would leave an inverted or singular F': no shortcut then)
+  }
+  // computePF with the polar rotation of particle.F supplied by the caller
+  __device__ __forceinline__ Mat computePF_R(Particle const& particle, Mat const& R) const {
+    real two_mu, lam_term;
+    mpm::hardened_lame<Ops>(this->mu0, this->lambda0, hardening, particle.Jp, two_mu, lam_term);
+    return mpm::corotated_PF(particle.F, R, two_mu, lam_term);
   }
 };
 

@@ -3,6 +3,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+#include <utility>
+
 #include "../../include/mpm_b200.h"
 #include "../../include/mpm_b200/InterpolationKernel.cuh"
 #include "../../include/mpm_b200/MaterialModel.cuh"
@@ -101,6 +104,27 @@ __device__ __forceinline__ Mat p2g_affine_dx(const Particle& particle, const Mat
     for (int j = 0; j < 3; ++j) A.m[i][j] = fmaf(kk, PF.m[i][j], s_c * particle.C.m[i][j]);
   return A;
 }
+
+// the affine matrix from a stress the caller already has
+template <class Material>
+__device__ __forceinline__ Mat p2g_affine_dx_from_PF(const Mat& PF, const Particle& particle, const Material& material, const KParams& k) {
+  const float kk = (((-k.dinv) * k.dt) * material.particleVolume) * k.dx;
+  const float s_c = material.particleMass * k.dx;
+  Mat A;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) A.m[i][j] = fmaf(kk, PF.m[i][j], s_c * particle.C.m[i][j]);
+  return A;
+}
+
+// does the material offer the rotation-sharing hooks (MaterialModel.cuh, MMSnow)?
+template <class M, class = void>
+struct HasRotationHooks : std::false_type {};
+template <class M>
+struct HasRotationHooks<M, std::void_t<decltype(std::declval<const M&>().endOfStepMutationR(std::declval<Particle&>(), std::declval<Mat&>())),
+                                       decltype(std::declval<const M&>().computePF_R(std::declval<const Particle&>(), std::declval<const Mat&>()))>>
+    : std::true_type {};
 
 // Materials as the kernels see them.  Single-material handles (the common case) read the material
 // from the kernel parameters (constant bank, no load latency: template flag ONE_MAT); the others

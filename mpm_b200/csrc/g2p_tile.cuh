@@ -215,7 +215,12 @@ __device__ __forceinline__ void g2p_tile_compute(const Soa& p, const MatTable<Ma
   if (kJp) part.Jp = ps[(SJ - SX) * kTile];
   else if (EMIT && with_jp) part.Jp = col[SJ * kTile];  // read-only Jp != 1 of a fixed-corotated handle
   const Material m = mats.template get<ONE_MAT>(p.mat, pi);
-  m.endOfStepMutation(part);
+  // hand-over: a material whose end-of-step hook decomposes F anyway (MMSnow) passes the rotation on to the
+  // stress of the next substep: one SVD per particle-step instead of the reference's two
+  constexpr bool kShareR = EMIT && HasRotationHooks<Material>::value;
+  Mat R;
+  bool have_R = false;
+  if constexpr (kShareR) have_R = m.endOfStepMutationR(part, R); else m.endOfStepMutation(part);
   if (kJp) MPM_STP(col + SJ * kTile, part.Jp);
   bool crossed = false;  // did the advection take the particle into another cell (rebin_permille, mpm_b200.h)
   int nbase[3];
@@ -234,7 +239,14 @@ __device__ __forceinline__ void g2p_tile_compute(const Soa& p, const MatTable<Ma
   if (EMIT) {
     // the next P2G skips a particle whose stencil has left the domain, and so does every G2P after
     // it: such a particle keeps C (the state the reference would hold), everyone else gets dx * affine
-    if (!stencil_outside(nbase, k.N)) out = p2g_affine_dx(part, m, k);
+    if (!stencil_outside(nbase, k.N)) {
+      if constexpr (kShareR) {
+        if (have_R) out = p2g_affine_dx_from_PF(m.computePF_R(part, R), part, m, k);
+        else out = p2g_affine_dx(part, m, k);
+      } else {
+        out = p2g_affine_dx(part, m, k);
+      }
+    }
   }
 #pragma unroll
   for (int r = 0; r < 3; ++r)
