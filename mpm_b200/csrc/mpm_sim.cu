@@ -148,6 +148,7 @@ struct MpmSim {
   };
   std::vector<GraphEntry> graphs;
   uint64_t graph_replays = 0;
+  bool capturing = false;  // inside a stream capture: no host-side read-backs
 
   Comm comm;
   std::string err;
@@ -251,6 +252,10 @@ struct StageTimer {
   }
 };
 
+// P2G re-orders its payload records warp by warp once this share of the particles (1 / divisor) has changed
+// cell since the last re-bin (G2P counts the crossings, the host reads the count back without waiting)
+constexpr unsigned long long kStaleOrderDivisor = 50;
+
 LaunchCtx make_ctx(MpmSim* sim) {
   LaunchCtx c{};
   c.stream = sim->stream;
@@ -266,6 +271,7 @@ LaunchCtx make_ctx(MpmSim* sim) {
   c.p2g_mode = (int)sim->par.p2g_mode;
   c.g2p_mode = (int)sim->par.g2p_mode;
   c.handover_in = sim->form_ad;
+  c.stale_order = sim->moved_seen * kStaleOrderDivisor >= (unsigned long long)sim->count && sim->count > 0;
   c.tile_begin = 0;
   c.tile_end = (sim->count + kTile - 1) / kTile;
   return c;
@@ -441,7 +447,7 @@ int do_g2p(MpmSim* sim, bool emit) {
   if (sim->count == 0) return 0;
   LaunchCtx c = make_ctx(sim);
   c.emit = emit;
-  c.moved = sim->par.rebin_permille ? sim->d_moved : nullptr;
+  c.moved = sim->d_moved;
   c.tile_counters = sim->d_tile_counters;
   c.tile_parity = sim->tile_parity;
   sim->ops->g2p(c);
@@ -799,20 +805,20 @@ int mpm_stage_g2p(MpmSim* sim) { if (!sim) return 1; drop_graphs(sim); CK(cudaSe
 static int advance_impl(MpmSim* sim, int n_substeps) {
   for (int s = 0; s < n_substeps; ++s) {
     bool due = sim->par.sort_every && sim->steps_since_sort >= sim->par.sort_every;
-    // (not for slab handles: every rank must reach the migration of a re-bin in the same substep)
-    const bool adaptive = sim->par.rebin_permille && sim->ops->staged && sim->par.g2p_mode == MPM_G2P_TILE && !sim->comm.active();
-    if (adaptive) {
-      // re-bin on measured disorder: the count of cell crossings since the last re-bin arrives a
-      // substep or two late (asynchronous read-back), which is early enough for a locality heuristic
-      // (the host may enqueue substeps far ahead of the device: a read-back older than 4 substeps is
-      // waited for, which also bounds that run-ahead)
-      if (sim->moved_pending && (sim->substeps - sim->moved_issued_at >= 4 || cudaEventQuery(sim->moved_ev) == cudaSuccess)) {
-        CK(cudaEventSynchronize(sim->moved_ev));
-        sim->moved_pending = false;
-        sim->moved_seen = *sim->h_moved;
-      }
-      due = due || (sim->steps_since_sort > 0 && sim->moved_seen * 1000ull >= (unsigned long long)sim->par.rebin_permille * sim->count && sim->count > 0);
+    // Cell crossings since the last re-bin, counted by the staged G2P and read back asynchronously (it
+    // arrives a substep or two late, early enough for heuristics; the host may enqueue substeps far
+    // ahead of the device: a read-back older than 4 substeps is waited for, which also bounds that
+    // run-ahead).  Drives the stale-order variant of P2G and, with rebin_permille, the re-bin itself
+    // (not on slab handles: every rank must reach the migration of a re-bin in the same substep).
+    const bool track = sim->ops->staged && sim->par.g2p_mode == MPM_G2P_TILE && !sim->capturing;
+    const bool adaptive = track && sim->par.rebin_permille && !sim->comm.active();
+    if (track && sim->moved_pending && (sim->substeps - sim->moved_issued_at >= 4 || cudaEventQuery(sim->moved_ev) == cudaSuccess)) {
+      CK(cudaEventSynchronize(sim->moved_ev));
+      sim->moved_pending = false;
+      sim->moved_seen = *sim->h_moved;
     }
+    if (adaptive)
+      due = due || (sim->steps_since_sort > 0 && sim->moved_seen * 1000ull >= (unsigned long long)sim->par.rebin_permille * sim->count && sim->count > 0);
     if (due) {  // the keys P2G writes come with fresh out-of-domain / non-finite counts
       CK(cudaMemsetAsync(&sim->d_diag->nonfinite, 0, 2 * sizeof(unsigned int), sim->stream));
     }
@@ -828,7 +834,7 @@ static int advance_impl(MpmSim* sim, int n_substeps) {
     }
     // hand-over: every G2P but the last of this call leaves the next P2G's affine matrix in the C rows
     if (int rc = do_g2p(sim, sim->handover && s + 1 < n_substeps)) return rc;
-    if (adaptive && !sim->moved_pending) {
+    if (track && !sim->moved_pending) {
       CK(cudaMemcpyAsync(sim->h_moved, sim->d_moved, sizeof(unsigned long long), cudaMemcpyDeviceToHost, sim->stream));
       CK(cudaEventRecord(sim->moved_ev, sim->stream));
       sim->moved_pending = true;
@@ -875,7 +881,9 @@ int mpm_advance(MpmSim* sim, int n_substeps) {
   const uint64_t rebins0 = sim->rebins, launches0 = sim->launches, substeps0 = sim->substeps;
   const double t0 = sim->t;
   CK(cudaStreamBeginCapture(sim->stream, cudaStreamCaptureModeThreadLocal));
+  sim->capturing = true;
   const int rc = advance_impl(sim, n_substeps);
+  sim->capturing = false;
   cudaGraph_t graph = nullptr;
   const cudaError_t ce = cudaStreamEndCapture(sim->stream, &graph);
   cudaGraphExec_t exec = nullptr;

@@ -33,6 +33,9 @@ namespace mpm {
 #ifndef MPM_P2G_MINBLK
 #define MPM_P2G_MINBLK 4
 #endif
+#ifndef MPM_P2G_WARPSORT_MIN
+#define MPM_P2G_WARPSORT_MIN 4  // descents in a warp's key sequence from which the warp sorts
+#endif
 #ifndef MPM_STREAM_HINTS
 #define MPM_STREAM_HINTS 1  // particle streams are touched once per kernel: evict-first loads
 #endif
@@ -70,21 +73,10 @@ __device__ __forceinline__ void bspline_w(float f, float w[3]) {
   w[2] = w[0] + a1;
 }
 
-// phase 0 tail: payload of one particle from its position, velocity and dx * affine.
+// phase 0 tail: payload of one particle from its fractional position f (cells, relative to the base
+// node), velocity and dx * affine.
 //   q(node) = m v + A (x_node - x) = q0 + i cx + j cy + k cz,  x_base - x = -dx f
-// Returns the packed biased base node, kInvalidKey for a particle outside the domain.
-__device__ __forceinline__ uint32_t p2g_store_payload(P2gSmem& sm, int tid, const float x[3], const float v[3], const Mat& Ad,
-                                                      float mass, const KParams& k, int base[3]) {
-  float f[3];
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    const float g = x[a] * k.dx_inv;
-    base[a] = (int)(g - 0.5f);  // C truncation like the reference's cast<int>()
-    f[a] = g - (float)base[a];
-  }
-  const bool inside = !stencil_outside(base, k.N);
-  const uint32_t key = inside ? (((uint32_t)(base[0] + kKeyBias) << 20) | ((uint32_t)(base[1] + kKeyBias) << 10) | (uint32_t)(base[2] + kKeyBias))
-                              : kInvalidKey;
+__device__ __forceinline__ void p2g_store_payload(P2gSmem& sm, int tid, const float f[3], const float v[3], const Mat& Ad, float mass) {
   float q0[3];
 #pragma unroll
   for (int c = 0; c < 3; ++c) q0[c] = v[c] * mass - (Ad.m[c][0] * f[0] + Ad.m[c][1] * f[1] + Ad.m[c][2] * f[2]);
@@ -94,7 +86,66 @@ __device__ __forceinline__ uint32_t p2g_store_payload(P2gSmem& sm, int tid, cons
   sm.pay[tid][3] = make_float4(Ad.m[2][1], q0[0] + Ad.m[0][2], q0[1] + Ad.m[1][2], q0[2] + Ad.m[2][2]);
   sm.pay[tid][4] = make_float4(Ad.m[2][1], fmaf(2.0f, Ad.m[0][2], q0[0]), fmaf(2.0f, Ad.m[1][2], q0[1]), fmaf(2.0f, Ad.m[2][2], q0[2]));
   sm.mass[tid] = mass;
-  return key;
+}
+
+// base node and packed run key of a position (kInvalidKey: the whole stencil lies outside the domain)
+__device__ __forceinline__ uint32_t p2g_key_of(const float x[3], const KParams& k, int base[3], float f[3]) {
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float g = x[a] * k.dx_inv;
+    base[a] = (int)(g - 0.5f);  // C truncation like the reference's cast<int>()
+    f[a] = g - (float)base[a];
+  }
+  if (stencil_outside(base, k.N)) return kInvalidKey;
+  return ((uint32_t)(base[0] + kKeyBias) << 20) | ((uint32_t)(base[1] + kKeyBias) << 10) | (uint32_t)(base[2] + kKeyBias);
+}
+
+// Stale order.  Between two re-bins the particles of a warp drift into neighbouring cells and the runs
+// of equal keys fragment (a sheared block at 0.1 cells per substep: 2.5 x the runs after 4 substeps).
+// A warp whose keys are no longer ascending sorts its 32 (key, lane) pairs with a bitonic network of
+// shuffles (15 compare-exchange steps) and writes its payload records in that order, which restores
+// one run per cell and warp; warps that are still in order (every warp right after a re-bin) pay one
+// shuffle and a vote.  pos = payload slot of this lane's particle within the warp, skey = the key at
+// slot `lane`.  scratch: kP2gBlock uint16 that nobody else uses before the next CTA barrier.
+// (out of line: the common, still-ordered path jumps over nothing and keeps its registers)
+static __device__ __noinline__ uint2 p2g_warp_sort(uint32_t key, int tid, uint16_t* scratch) {
+  const int lane = tid & 31;
+  uint32_t kk = key;
+  int src = lane;
+#pragma unroll
+  for (int k2 = 2; k2 <= 32; k2 <<= 1)
+#pragma unroll
+    for (int j = k2 >> 1; j > 0; j >>= 1) {
+      const uint32_t pk = __shfl_xor_sync(0xffffffffu, kk, j);
+      const int ps = __shfl_xor_sync(0xffffffffu, src, j);
+      const bool up = (lane & k2) == 0, lower = (lane & j) == 0;
+      const bool partner_less = pk < kk || (pk == kk && ps < src);  // (key, lane) pairs are distinct: a strict order
+      if ((lower == up) ? partner_less : !partner_less) {
+        kk = pk;
+        src = ps;
+      }
+    }
+  scratch[(tid & ~31) + src] = (uint16_t)lane;  // this lane now holds the pair that came from lane `src`: its rank is `lane`
+  __syncwarp();
+  const uint32_t pos = scratch[tid];
+  __syncwarp();
+  return make_uint2(pos, kk);
+}
+template <bool SORT>
+__device__ __forceinline__ void p2g_warp_order(uint32_t key, int tid, uint16_t* scratch, int& pos, uint32_t& skey) {
+  const int lane = tid & 31;
+  pos = lane;
+  skey = key;
+  if constexpr (SORT) {
+    // (one or two stragglers do not pay for a sort: the warp's sort delays its whole CTA at the next barrier,
+    // profiles/r02_ab4_p2g_warpsort.txt)
+    const uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
+    if (__popc(__ballot_sync(0xffffffffu, lane > 0 && prev > key)) >= MPM_P2G_WARPSORT_MIN) {
+      const uint2 r = p2g_warp_sort(key, tid, scratch);
+      pos = (int)r.x;
+      skey = r.y;
+    }
+  }
 }
 
 // phase R: warp-local runs of equal keys, listed block-wide in order of descending length.
@@ -223,7 +274,9 @@ struct MaterialTraits<MMFixedCorotated<P, O>> {
 // in the same substep — the positions are in registers here anyway, which saves the sort its own pass
 // over them (cell_key_kernel, sort.cuh; same key: clamped base node, x local to the slab, z fastest) —
 // and count non-finite / out-of-domain particles for mpm_get_diagnostics.
-template <class Material, bool ONE_MAT, bool HANDOVER>
+// SORT: the launch was told that the order has gone stale (the host decides from the cell crossings G2P
+// counts since the last re-bin): warps re-order their payload records first (p2g_warp_order)
+template <class Material, bool ONE_MAT, bool HANDOVER, bool SORT>
 __global__ void __launch_bounds__(kP2gBlock, MPM_P2G_MINBLK)
 p2g_sched_kernel(Soa p, size_t count, const MatTable<Material> mats, float4* __restrict__ grid, KParams k,
                  uint32_t* __restrict__ sort_keys, uint32_t* __restrict__ sort_vals, uint32_t first, DeviceDiag* __restrict__ diag) {
@@ -234,31 +287,42 @@ p2g_sched_kernel(Soa p, size_t count, const MatTable<Material> mats, float4* __r
   __syncthreads();
 
   // ---------------- phase 0: per-particle payload ----------------
-  uint32_t key = kInvalidKey;
-  if (pi < count) {
-    const float* __restrict__ col = p.tile(blockIdx.x) + tid;
-    float x[3], v[3];
+  // (all loads are issued before anything waits for one of them: one DRAM round trip per CTA)
+  const float* __restrict__ col = p.tile(blockIdx.x) + tid;
+  const bool live = pi < count;
+  float x[3] = {0.f, 0.f, 0.f}, v[3] = {0.f, 0.f, 0.f};
+  Mat A = Mat::Zero();  // C, or dx * affine when handed over
+  Particle part;
+  part.material_type = 0;
+  part.Jp = 1.0f;
+  if (live) {
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
       x[a] = MPM_LDP(col + (SX + a) * kTile);
       v[a] = MPM_LDP(col + (SV + a) * kTile);
     }
-    Mat A;  // C, or dx * affine when handed over
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
       for (int c = 0; c < 3; ++c) A.m[r][c] = MPM_LDP(col + (SC + 3 * r + c) * kTile);
-    const Material m = mats.template get<ONE_MAT>(p.mat, pi);
     if constexpr (!HANDOVER) {
-      Particle part;
-      part.material_type = 0;
 #pragma unroll
       for (int r = 0; r < 3; ++r)
 #pragma unroll
         for (int c = 0; c < 3; ++c) part.F.m[r][c] = MPM_LDP(col + (SF + 3 * r + c) * kTile);
-      part.C = A;
-      part.Jp = 1.0f;
       if (MaterialTraits<Material>::kMutatesJp || diag->jp_not_one) part.Jp = MPM_LDP(col + SJ * kTile);
+    }
+  }
+  int base[3] = {0, 0, 0};
+  float f[3] = {0.f, 0.f, 0.f};
+  const uint32_t key = live ? p2g_key_of(x, k, base, f) : kInvalidKey;
+  int pos;
+  uint32_t skey;
+  p2g_warp_order<SORT>(key, tid, sm.runs, pos, skey);
+  if (live) {
+    const Material m = mats.template get<ONE_MAT>(p.mat, pi);
+    if constexpr (!HANDOVER) {
+      part.C = A;
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
         part.x(a) = x[a];
@@ -266,8 +330,7 @@ p2g_sched_kernel(Soa p, size_t count, const MatTable<Material> mats, float4* __r
       }
       A = p2g_affine_dx(part, m, k);
     }
-    int base[3];
-    key = p2g_store_payload(sm, tid, x, v, A, m.particleMass, k, base);
+    p2g_store_payload(sm, (tid & ~31) + pos, f, v, A, m.particleMass);
     if (key != kInvalidKey) {  // slab handles: a stencil that leaves the planes held here loses mass
       const int lo = max(base[0], 0), hi = min(base[0] + 2, k.N - 1);
       if (lo < k.x0 || hi >= k.x0 + k.nxl) atomicAdd(&diag->escaped, 1u);
@@ -283,8 +346,8 @@ p2g_sched_kernel(Soa p, size_t count, const MatTable<Material> mats, float4* __r
       else if (key == kInvalidKey) atomicAdd(&diag->out_of_domain, 1u);
     }
   }
-  sm.key[tid] = key;
-  const int n_runs = p2g_list_runs(sm, key, tid);
+  sm.key[tid] = skey;  // the key of the record in slot tid
+  const int n_runs = p2g_list_runs(sm, skey, tid);
   p2g_scatter_runs<ONE_MAT>(sm, n_runs, tid, grid, k, mats.one.particleMass);
 }
 

@@ -34,6 +34,7 @@ struct LaunchCtx {
   // P2G
   bool handover_in;           // the C rows hold dx * affine (written by the previous G2P)
   size_t tile_begin, tile_end;  // tiles [begin, end) of the SoA (split launches of slab handles)
+  bool stale_order;           // enough particles changed cell since the last re-bin: warps re-order their records
   uint32_t* sort_keys;        // non-null: also emit the cell keys of the re-bin that follows
   uint32_t* sort_vals;
   // G2P
@@ -71,7 +72,7 @@ struct ModelImpl {
     return t;
   }
 
-  template <bool ONE_MAT, bool HANDOVER>
+  template <bool ONE_MAT, bool HANDOVER, bool SORT>
   static void p2g_sched(const LaunchCtx& c) {
     Soa view = c.soa;
     view.f += c.tile_begin * (size_t)kTileFloats;  // the kernel indexes tiles and ids from its first block
@@ -79,7 +80,7 @@ struct ModelImpl {
     view.mat += c.tile_begin * kTile;
     const size_t first = c.tile_begin * kTile;
     const size_t n = std::min(c.count, c.tile_end * kTile) - first;
-    p2g_sched_kernel<Material, ONE_MAT, HANDOVER><<<(unsigned)(c.tile_end - c.tile_begin), kP2gBlock, 0, c.stream>>>(
+    p2g_sched_kernel<Material, ONE_MAT, HANDOVER, SORT><<<(unsigned)(c.tile_end - c.tile_begin), kP2gBlock, 0, c.stream>>>(
         view, n, table(c), c.grid, c.k, c.sort_keys ? c.sort_keys + first : nullptr, c.sort_vals ? c.sort_vals + first : nullptr,
         (uint32_t)first, c.diag);
   }
@@ -89,8 +90,13 @@ struct ModelImpl {
     if constexpr (kStaged) {
       if (c.p2g_mode == MPM_P2G_RUNS && c.k.N <= kP2gMaxN) {
         const bool one = c.n_mats == 1;
-        if (c.handover_in) one ? p2g_sched<true, true>(c) : p2g_sched<false, true>(c);
-        else one ? p2g_sched<true, false>(c) : p2g_sched<false, false>(c);
+        if (c.stale_order) {
+          if (c.handover_in) one ? p2g_sched<true, true, true>(c) : p2g_sched<false, true, true>(c);
+          else one ? p2g_sched<true, false, true>(c) : p2g_sched<false, false, true>(c);
+        } else {
+          if (c.handover_in) one ? p2g_sched<true, true, false>(c) : p2g_sched<false, true, false>(c);
+          else one ? p2g_sched<true, false, false>(c) : p2g_sched<false, false, false>(c);
+        }
         return;
       }
     }
