@@ -158,6 +158,7 @@ uint64_t mpm_substeps_done(const MpmSim* sim);
 uint64_t mpm_kernel_launches(const MpmSim* sim); /* kernels this handle has launched so far */
 uint64_t mpm_rebins_done(const MpmSim* sim);     /* re-bins (sort + permute) so far, the one at upload included */
 uint64_t mpm_graph_replays(const MpmSim* sim);   /* mpm_advance calls served by replaying a captured CUDA graph */
+uint64_t mpm_merge_rebins(const MpmSim* sim);    /* re-bins done by merging (few particles changed cell) instead of the radix sort */
 
 /* single stages, for parity tests and profiling (same kernels mpm_advance runs) */
 int mpm_stage_sort(MpmSim* sim);        /* north-star stage (1): cell keys, radix sort, SoA permute */

@@ -63,6 +63,8 @@ def lib():
         L.mpm_rebins_done.argtypes = [_vp]
         L.mpm_graph_replays.restype = ctypes.c_uint64
         L.mpm_graph_replays.argtypes = [_vp]
+        L.mpm_merge_rebins.restype = ctypes.c_uint64
+        L.mpm_merge_rebins.argtypes = [_vp]
         L.mpm_stream.restype = _vp
         L.mpm_stream.argtypes = [_vp]
         L.mpm_destroy.restype = None
@@ -226,6 +228,10 @@ class Sim:
     @property
     def graph_replays(self):
         return lib().mpm_graph_replays(self._h)
+
+    @property
+    def merge_rebins(self):
+        return lib().mpm_merge_rebins(self._h)
 
     @property
     def stream(self):

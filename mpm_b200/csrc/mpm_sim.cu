@@ -96,7 +96,21 @@ struct MpmSim {
   int key_bits = 0;
   int ghost = 0;
   bool whole_domain = true;
-  int sorted_cur = 0;  // which keys[] buffer holds the keys of the current order
+  // the sorted cell keys of the CURRENT particle order (valid for the first okeys_count slots) and a 1/64
+  // sample of them: the merge re-bin compares them with the new keys (sort.cuh)
+  uint32_t* okeys[2] = {nullptr, nullptr};
+  int ocur = 0;
+  size_t okeys_count = 0;
+  uint32_t* ocoarse = nullptr;
+  // merge re-bin scratch: ballot words + their prefix counts, per-tile moved counts, the moved pairs
+  uint32_t* mmask = nullptr;
+  uint32_t* wprefix = nullptr;
+  uint32_t* tile_moved = nullptr;
+  uint32_t* mk[2] = {nullptr, nullptr};
+  uint32_t* mi[2] = {nullptr, nullptr};
+  size_t moved_cap = 0;
+  uint32_t* d_n_moved = nullptr;
+  uint64_t merge_rebins = 0;
 
   MpmParticle* aos_stage = nullptr;  // device AoS staging for upload/download
   size_t aos_stage_cap = 0;
@@ -138,12 +152,12 @@ struct MpmSim {
   // CUDA graphs of whole mpm_advance calls (MpmParams.graph_mode), keyed by everything the launch
   // sequence depends on; dropped whenever anything but mpm_advance touches the handle
   struct GraphEntry {
-    int n_substeps, cur, sorted_cur, tile_parity;
+    int n_substeps, cur, ocur, tile_parity;
     uint64_t steps_since_sort;
     size_t count;
     cudaGraphExec_t exec;
     // host state after the call
-    int cur_after, sorted_cur_after, tile_parity_after;
+    int cur_after, ocur_after, tile_parity_after;
     uint64_t steps_since_sort_after, rebins_delta, launches_delta;
   };
   std::vector<GraphEntry> graphs;
@@ -196,6 +210,15 @@ int ensure_capacity(MpmSim* sim, size_t cap) {
     }
     cudaFree(sim->table);
     cudaFree(sim->scan_sums);
+    for (int b = 0; b < 2; ++b) {
+      cudaFree(sim->okeys[b]);
+      cudaFree(sim->mk[b]);
+      cudaFree(sim->mi[b]);
+    }
+    cudaFree(sim->ocoarse);
+    cudaFree(sim->mmask);
+    cudaFree(sim->wprefix);
+    cudaFree(sim->tile_moved);
   }
   cap = (cap + kTile - 1) / kTile * kTile;
   for (int b = 0; b < 2; ++b) {
@@ -208,6 +231,17 @@ int ensure_capacity(MpmSim* sim, size_t cap) {
   CK(cudaMalloc(&sim->table, sizeof(uint32_t) * sim->table_len));
   sim->scan_sums_len = (sim->table_len + kScanTile - 1) / kScanTile;
   CK(cudaMalloc(&sim->scan_sums, sizeof(uint32_t) * sim->scan_sums_len));
+  sim->moved_cap = cap / 8 + 4096;  // the merge re-bin is taken up to an eighth of the particles moved
+  for (int b = 0; b < 2; ++b) {
+    CK(cudaMalloc(&sim->okeys[b], sizeof(uint32_t) * cap));
+    CK(cudaMalloc(&sim->mk[b], sizeof(uint32_t) * sim->moved_cap));
+    CK(cudaMalloc(&sim->mi[b], sizeof(uint32_t) * sim->moved_cap));
+  }
+  CK(cudaMalloc(&sim->ocoarse, sizeof(uint32_t) * (cap / kCoarse + 2)));
+  CK(cudaMalloc(&sim->mmask, sizeof(uint32_t) * (cap / 32 + 4)));
+  CK(cudaMalloc(&sim->wprefix, sizeof(uint32_t) * (cap / 32 + 4)));
+  CK(cudaMalloc(&sim->tile_moved, sizeof(uint32_t) * (cap / kMergeTile + 4)));
+  sim->okeys_count = 0;
   sim->capacity = cap;
   return 0;
 }
@@ -278,29 +312,90 @@ LaunchCtx make_ctx(MpmSim* sim) {
 }
 
 // ---- stages -------------------------------------------------------------------------------------
+// one pass of the stable LSD radix sort: (kin, vin) -> (kout, vout) by the digit at `shift`
 template <int BITS>
-void radix_pass(MpmSim* sim, int in, size_t n, int shift, int n_tiles) {
+void radix_pass(MpmSim* sim, const uint32_t* kin, const uint32_t* vin, uint32_t* kout, uint32_t* vout, size_t n, int shift, int n_tiles) {
   const size_t table_len = (size_t)n_tiles << BITS;
   const unsigned scan_blocks = blocks_for(table_len, kScanTile);
-  radix_hist_kernel<BITS><<<n_tiles, kSortThreads, 0, sim->stream>>>(sim->keys[in], n, shift, sim->table, n_tiles);
+  radix_hist_kernel<BITS><<<n_tiles, kSortThreads, 0, sim->stream>>>(kin, n, shift, sim->table, n_tiles);
   scan_tile_sums_kernel<<<scan_blocks, kScanThreads, 0, sim->stream>>>(sim->table, table_len, sim->scan_sums);
   scan_sums_kernel<<<1, 1024, 0, sim->stream>>>(sim->scan_sums, scan_blocks);
   scan_downsweep_kernel<<<scan_blocks, kScanThreads, 0, sim->stream>>>(sim->table, table_len, sim->scan_sums);
-  radix_scatter_kernel<BITS><<<n_tiles, kSortThreads, 0, sim->stream>>>(sim->keys[in], sim->vals[in], sim->keys[in ^ 1], sim->vals[in ^ 1], n,
-                                                                       shift, sim->table, n_tiles);
+  radix_scatter_kernel<BITS><<<n_tiles, kSortThreads, 0, sim->stream>>>(kin, vin, kout, vout, n, shift, sim->table, n_tiles);
   sim->launches += 5;
 }
 
-// stable LSD radix sort of the (key, index) pairs in keys[0] / vals[0]; returns the buffer that holds the result
-int sort_pairs(MpmSim* sim, size_t n) {
+// Stable LSD radix sort of n (key, value) pairs over `key_bits` bits between the buffer pairs k[2] / v[2],
+// starting in k[0] / v[0]; returns the index of the pair that holds the result.  final_keys (optional): the
+// last pass writes the sorted keys there instead.
+int radix_sort(MpmSim* sim, uint32_t* const k[2], uint32_t* const v[2], size_t n, int key_bits, uint32_t* final_keys = nullptr) {
   const int n_tiles = (int)((n + kSortTile - 1) / kSortTile);
-  const int bits = radix_bits(sim->key_bits);
+  const int bits = radix_bits(key_bits);
   int in = 0;
-  for (int shift = 0; shift < sim->key_bits; shift += bits) {
-    if (bits == 8) radix_pass<8>(sim, in, n, shift, n_tiles); else radix_pass<9>(sim, in, n, shift, n_tiles);
+  for (int shift = 0; shift < key_bits; shift += bits) {
+    uint32_t* kout = (final_keys && shift + bits >= key_bits) ? final_keys : k[in ^ 1];
+    if (bits == 8) radix_pass<8>(sim, k[in], v[in], kout, v[in ^ 1], n, shift, n_tiles);
+    else radix_pass<9>(sim, k[in], v[in], kout, v[in ^ 1], n, shift, n_tiles);
     in ^= 1;
   }
   return in;
+}
+
+// Sorts the pairs in keys[0] / vals[0]: the sorted keys go to okeys[ocur ^ 1] (which becomes current), the
+// permutation to the returned buffer.
+uint32_t* sort_pairs(MpmSim* sim, size_t n) {
+  const int in = radix_sort(sim, sim->keys, sim->vals, n, sim->key_bits, sim->okeys[sim->ocur ^ 1]);
+  sim->ocur ^= 1;
+  sim->okeys_count = n;
+  coarse_keys_kernel<<<blocks_for((n + kCoarse - 1) / kCoarse, 256), 256, 0, sim->stream>>>(sim->okeys[sim->ocur], (uint32_t)n, sim->ocoarse);
+  sim->launches++;
+  return sim->vals[in];
+}
+
+// The same result by merging (sort.cuh, "merge re-bin"): keys[0] holds the new keys of the particles in their
+// current order, okeys[ocur] the keys they were sorted by.  Counts the particles whose key changed (one host
+// synchronisation: the count sizes the launches that follow); with more than an eighth of them changed it
+// returns nullptr and the caller radix-sorts.  Sorted keys to okeys[ocur ^ 1], permutation to vals[1].
+uint32_t* merge_pairs(MpmSim* sim, size_t n, size_t n_old, int* rc) {
+  *rc = 0;
+  const uint32_t* newk = sim->keys[0];
+  const uint32_t* oldk = sim->okeys[sim->ocur];
+  uint32_t* keys_out = sim->okeys[sim->ocur ^ 1];
+  uint32_t* perm = sim->vals[1];
+  const unsigned n_tiles = blocks_for(n, kMergeTile);
+  rebin_flags_kernel<<<n_tiles, kMergeThreads, 0, sim->stream>>>(newk, oldk, (uint32_t)n, (uint32_t)n_old, sim->mmask, sim->tile_moved);
+  exclusive_scan_total_kernel<<<1, 1024, 0, sim->stream>>>(sim->tile_moved, n_tiles, sim->d_n_moved);
+  sim->launches += 2;
+  uint32_t* h_n = reinterpret_cast<uint32_t*>(sim->h_moved);  // pinned scratch
+  if (cudaMemcpyAsync(h_n, sim->d_n_moved, sizeof(uint32_t), cudaMemcpyDeviceToHost, sim->stream) != cudaSuccess ||
+      cudaStreamSynchronize(sim->stream) != cudaSuccess) {
+    *rc = 1;
+    return nullptr;
+  }
+  const size_t n_moved = *h_n;
+  if (n_moved * 8 > n || n_moved > sim->moved_cap) return nullptr;
+  rebin_compact_kernel<<<n_tiles, kMergeThreads, 0, sim->stream>>>(newk, (uint32_t)n, sim->mmask, sim->tile_moved, sim->wprefix, sim->mk[0], sim->mi[0],
+                                                                  (uint32_t)n_moved, sim->d_n_moved);
+  sim->launches++;
+  int in = 0;
+  if (n_moved) {
+    in = radix_sort(sim, sim->mk, sim->mi, n_moved, sim->key_bits);
+    rebin_place_moved_kernel<<<blocks_for(n_moved, 256), 256, 0, sim->stream>>>(sim->mk[in], sim->mi[in], (uint32_t)n_moved, oldk, sim->ocoarse,
+                                                                             (uint32_t)n_old, sim->mmask, sim->wprefix, perm, keys_out);
+    sim->launches++;
+  }
+  uint32_t* slice_begin = sim->tile_moved;  // (the compaction is done with it)
+  rebin_tile_slices_kernel<<<blocks_for(n_tiles + 1, 128), 128, 0, sim->stream>>>(newk, (uint32_t)n, sim->mmask, sim->mk[in], sim->mi[in],
+                                                                                 (uint32_t)n_moved, n_tiles, slice_begin);
+  rebin_place_stayed_kernel<<<n_tiles, kMergeThreads, 0, sim->stream>>>(newk, (uint32_t)n, sim->mmask, sim->wprefix, sim->mk[in], sim->mi[in],
+                                                                       slice_begin, perm, keys_out);
+  sim->launches++;
+  sim->ocur ^= 1;
+  sim->okeys_count = n;
+  coarse_keys_kernel<<<blocks_for((n + kCoarse - 1) / kCoarse, 256), 256, 0, sim->stream>>>(sim->okeys[sim->ocur], (uint32_t)n, sim->ocoarse);
+  sim->launches += 2;
+  sim->merge_rebins++;
+  return perm;
 }
 
 // partial: called between the grid update and G2P, permutes only what G2P reads (sort.cuh)
@@ -308,20 +403,24 @@ int do_sort(MpmSim* sim, bool partial = false, bool keys_ready = false) {
   StageTimer tm(sim, MPM_STAGE_SORT);
   sim->steps_since_sort = 0;
   sim->rebins++;
+  const bool merge_allowed = partial && !sim->capturing;
+  const unsigned long long crossings_estimate = sim->moved_seen;  // a substep or two old: good enough to skip hopeless attempts
   sim->moved_seen = 0;
   sim->moved_pending = false;
   if (sim->d_moved) CK(cudaMemsetAsync(sim->d_moved, 0, sizeof(unsigned long long), sim->stream));
-  size_t n_dead = 0;
+  size_t n_dead = 0, n_arrived = 0;
   if (sim->comm.active()) {  // leavers out (tombstoned), arrivals appended, before the re-bin
     // particles whose stencil left the planes held here since the last re-bin lost mass on the grid:
     // that is a configuration error (ghost width / re-bin cadence too small for the velocities), and
     // every rank must stop for it, not only the one that saw it
     unsigned int escaped = 0;
+    const size_t count_before = sim->count;
     // (with the cell keys P2G wrote for this re-bin: leavers' keys become the tombstone key, arrivals get theirs)
     if (sim->comm.migrate(sim->soa[sim->cur], &sim->count, sim->capacity, sim->k, sim->stream, &sim->launches, &n_dead, &sim->d_diag->escaped,
                           &escaped, keys_ready ? sim->keys[0] : nullptr, keys_ready ? sim->vals[0] : nullptr, (uint32_t)sim->grid_nodes))
       return fail(sim, "particle migration failed: %s", sim->comm.error());
     CK(cudaMemsetAsync(&sim->d_diag->escaped, 0, sizeof(unsigned int), sim->stream));
+    n_arrived = sim->count - count_before;
     if (escaped)
       return fail(sim, "%u particle-substeps (all ranks) scattered outside the %d ghost plane(s) of their slab since the last re-bin; "
                        "this rank holds [%d,%d): raise MpmParams.ghost or lower sort_every", escaped, sim->ghost, sim->k.x_own_begin, sim->k.x_own_end);
@@ -334,11 +433,20 @@ int do_sort(MpmSim* sim, bool partial = false, bool keys_ready = false) {
     cell_key_kernel<<<blocks_for(n, 256), 256, 0, sim->stream>>>(src, n, sim->k, sim->keys[0], sim->vals[0], dead_key);
     sim->launches++;
   }
-  const int in = sort_pairs(sim, n);
-  sim->sorted_cur = in;
+  // Merge when few particles changed cell (the last read-back of G2P's crossing count says whether the attempt
+  // is worth its counting pass; the decision itself rests on the exact number of changed keys).  Otherwise —
+  // upload, DIRECT kernels, fast flows, while a graph is being captured — the radix sort.
+  const uint32_t* perm = nullptr;
+  const size_t n_old = n - n_arrived;
+  if (keys_ready && merge_allowed && sim->okeys_count >= n_old && n >= (size_t)kMergeTile && crossings_estimate * 6 <= n) {
+    int rc = 0;
+    perm = merge_pairs(sim, n, n_old, &rc);
+    if (rc) return fail(sim, "merge re-bin: reading the moved count back failed");
+  }
+  if (!perm) perm = sort_pairs(sim, n);
   Soa& dst = sim->soa[sim->cur ^ 1];
-  if (partial) permute_kernel<true><<<blocks_for(n, 256), 256, 0, sim->stream>>>(src, dst, sim->vals[in], n, sim->k);
-  else permute_kernel<false><<<blocks_for(n, 256), 256, 0, sim->stream>>>(src, dst, sim->vals[in], n, sim->k);
+  if (partial) permute_kernel<true><<<blocks_for(n, 256), 256, 0, sim->stream>>>(src, dst, perm, n, sim->k);
+  else permute_kernel<false><<<blocks_for(n, 256), 256, 0, sim->stream>>>(src, dst, perm, n, sim->k);
   sim->launches++;
   sim->cur ^= 1;
   sim->count = n - n_dead;  // tombstones were sorted behind the live particles
@@ -348,7 +456,7 @@ int do_sort(MpmSim* sim, bool partial = false, bool keys_ready = false) {
     const uint32_t NN = (uint32_t)sim->k.N * (uint32_t)sim->k.N;
     const uint32_t key_lo = sim->comm.has_lo ? (uint32_t)(sim->k.x_own_begin + 2 + 2 * g - sim->k.x0) * NN : 0u;
     const uint32_t key_hi = sim->comm.has_hi ? (uint32_t)std::max(0, sim->k.x_own_end - 2 - 2 * g - sim->k.x0) * NN : 0xffffffffu;
-    split_bounds_kernel<<<1, 32, 0, sim->stream>>>(sim->keys[in], (uint32_t)sim->count, key_lo, key_hi, sim->d_split);
+    split_bounds_kernel<<<1, 32, 0, sim->stream>>>(sim->okeys[sim->ocur], (uint32_t)sim->count, key_lo, key_hi, sim->d_split);
     sim->launches++;
     CK(cudaMemcpyAsync(sim->h_split, sim->d_split, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, sim->stream));
     CK(cudaEventRecord(sim->split_ev, sim->stream));
@@ -576,6 +684,7 @@ int mpm_create_raw(const MpmParams* params, const void* materials, size_t materi
   CKC(cudaMalloc(&sim->mats_dev, material_bytes * (size_t)n_materials));
   CKC(cudaMemcpy(sim->mats_dev, materials, material_bytes * (size_t)n_materials, cudaMemcpyHostToDevice));
   CKC(cudaMalloc(&sim->d_counter, sizeof(unsigned long long)));
+  CKC(cudaMalloc(&sim->d_n_moved, sizeof(uint32_t)));
   CKC(cudaMalloc(&sim->d_diag, sizeof(DeviceDiag)));
   CKC(cudaMemsetAsync(sim->d_diag, 0, sizeof(DeviceDiag), sim->stream));
   CKC(cudaMallocHost(&sim->h_diag, sizeof(DeviceDiag)));
@@ -622,6 +731,16 @@ void mpm_destroy(MpmSim* sim) {
   }
   cudaFree(sim->table);
   cudaFree(sim->scan_sums);
+  for (int b = 0; b < 2; ++b) {
+    cudaFree(sim->okeys[b]);
+    cudaFree(sim->mk[b]);
+    cudaFree(sim->mi[b]);
+  }
+  cudaFree(sim->ocoarse);
+  cudaFree(sim->mmask);
+  cudaFree(sim->wprefix);
+  cudaFree(sim->tile_moved);
+  cudaFree(sim->d_n_moved);
   cudaFree(sim->grid);
   cudaFree(sim->mats_dev);
   free(sim->mats_host);
@@ -669,9 +788,8 @@ static int upload_impl(MpmSim* sim, const MpmParticle* particles, size_t count, 
     sim->moved_pending = false;
     CK(cudaMemsetAsync(sim->d_moved, 0, sizeof(unsigned long long), sim->stream));
     aos_keys_kernel<<<blocks_for(count, 256), 256, 0, sim->stream>>>(sim->aos_stage, count, sim->k, sim->keys[0], sim->vals[0], sim->d_diag);
-    const int in = sort_pairs(sim, count);
-    sim->sorted_cur = in;
-    aos_gather_to_soa_kernel<<<blocks_for(count, kTile), kTile, 0, sim->stream>>>(sim->aos_stage, sim->vals[in], sim->soa[0], count, 0);
+    const uint32_t* perm = sort_pairs(sim, count);
+    aos_gather_to_soa_kernel<<<blocks_for(count, kTile), kTile, 0, sim->stream>>>(sim->aos_stage, perm, sim->soa[0], count, 0);
     sim->launches += 2;
     CK(cudaGetLastError());
     return 0;
@@ -792,6 +910,7 @@ uint64_t mpm_substeps_done(const MpmSim* sim) { return sim ? sim->substeps : 0; 
 uint64_t mpm_kernel_launches(const MpmSim* sim) { return sim ? sim->launches : 0; }
 uint64_t mpm_rebins_done(const MpmSim* sim) { return sim ? sim->rebins : 0; }
 uint64_t mpm_graph_replays(const MpmSim* sim) { return sim ? sim->graph_replays : 0; }
+uint64_t mpm_merge_rebins(const MpmSim* sim) { return sim ? sim->merge_rebins : 0; }
 void* mpm_stream(MpmSim* sim) { return sim ? (void*)sim->stream : nullptr; }
 
 // single stages, for parity tests and profiling: the same kernels mpm_advance runs, on particles in
@@ -855,11 +974,11 @@ int mpm_advance(MpmSim* sim, int n_substeps) {
   const bool graphable = want && sim->count > 0 && n_substeps <= 256 && !sim->par.rebin_permille && !sim->comm.active() && !sim->timing;
   if (!graphable) return advance_impl(sim, n_substeps);
   for (auto& g : sim->graphs) {
-    if (g.n_substeps == n_substeps && g.cur == sim->cur && g.sorted_cur == sim->sorted_cur && g.tile_parity == sim->tile_parity &&
+    if (g.n_substeps == n_substeps && g.cur == sim->cur && g.ocur == sim->ocur && g.tile_parity == sim->tile_parity &&
         g.steps_since_sort == sim->steps_since_sort && g.count == sim->count) {
       CK(cudaGraphLaunch(g.exec, sim->stream));
       sim->cur = g.cur_after;
-      sim->sorted_cur = g.sorted_cur_after;
+      sim->ocur = g.ocur_after;
       sim->tile_parity = g.tile_parity_after;
       sim->steps_since_sort = g.steps_since_sort_after;
       sim->rebins += g.rebins_delta;
@@ -874,7 +993,7 @@ int mpm_advance(MpmSim* sim, int n_substeps) {
   MpmSim::GraphEntry e{};
   e.n_substeps = n_substeps;
   e.cur = sim->cur;
-  e.sorted_cur = sim->sorted_cur;
+  e.ocur = sim->ocur;
   e.tile_parity = sim->tile_parity;
   e.steps_since_sort = sim->steps_since_sort;
   e.count = sim->count;
@@ -891,7 +1010,7 @@ int mpm_advance(MpmSim* sim, int n_substeps) {
     cudaGraphDestroy(graph);
     e.exec = exec;
     e.cur_after = sim->cur;
-    e.sorted_cur_after = sim->sorted_cur;
+    e.ocur_after = sim->ocur;
     e.tile_parity_after = sim->tile_parity;
     e.steps_since_sort_after = sim->steps_since_sort;
     e.rebins_delta = sim->rebins - rebins0;
@@ -908,7 +1027,7 @@ int mpm_advance(MpmSim* sim, int n_substeps) {
   if (graph) cudaGraphDestroy(graph);
   cudaGetLastError();
   sim->cur = e.cur;
-  sim->sorted_cur = e.sorted_cur;
+  sim->ocur = e.ocur;
   sim->tile_parity = e.tile_parity;
   sim->steps_since_sort = e.steps_since_sort;
   sim->rebins = rebins0;
@@ -962,7 +1081,7 @@ int mpm_debug_download_sort(MpmSim* sim, uint32_t* keys, uint32_t* ids, size_t c
   CK(cudaSetDevice(sim->device));
   if (capacity < sim->count) return fail(sim, "capacity too small");
   if (sim->count == 0) return 0;
-  if (keys) CK(cudaMemcpyAsync(keys, sim->keys[sim->sorted_cur], sizeof(uint32_t) * sim->count, cudaMemcpyDeviceToHost, sim->stream));
+  if (keys) CK(cudaMemcpyAsync(keys, sim->okeys[sim->ocur], sizeof(uint32_t) * sim->count, cudaMemcpyDeviceToHost, sim->stream));
   if (ids) CK(cudaMemcpyAsync(ids, sim->soa[sim->cur].id, sizeof(uint32_t) * sim->count, cudaMemcpyDeviceToHost, sim->stream));
   CK(cudaStreamSynchronize(sim->stream));
   return 0;

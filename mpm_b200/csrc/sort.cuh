@@ -244,6 +244,270 @@ __global__ void __launch_bounds__(256) permute_kernel(Soa src, Soa dst, const ui
   }
 }
 
+// ---- merge re-bin -------------------------------------------------------------------------------------
+// Between two re-bins most particles stay in their cell.  Those form a subsequence of the current order
+// that is ALREADY sorted by the new keys (their new key is their old one), so the stable sort of the whole
+// sequence is the merge of that subsequence with the (few) particles whose key changed, sorted among
+// themselves by (key, current index):
+//   1. flags: moved[i] = new key != old key (or no old key: arrivals of a slab handle); one ballot word per
+//      32 particles + its prefix count, so that "moved before position p" is an O(1) lookup;
+//   2. the host reads the moved count back (it sizes the launches that follow; above an eighth of the
+//      particles the radix sort takes over); the moved (key, index) pairs are compacted and radix-sorted;
+//   3. a moved pair's final position = its rank among the moved + the number of stayed particles that
+//      precede it, found by binary search in the OLD sorted keys (two levels: a 1/64 sample first);
+//   4. a stayed particle's final position = its rank among the stayed + the number of moved pairs that
+//      precede it, found in the slice of the sorted moved list that its 2048-particle tile can see
+//      (one search per tile bounds the slice, which is then staged in shared memory).
+// The result (keys and permutation) is identical to the LSD radix sort's, for a fraction of the traffic when
+// few particles moved.
+constexpr int kMergeTile = 2048;
+constexpr int kMergeThreads = 256;
+constexpr int kCoarse = 64;                 // sampling stride of the old keys for the two-level search
+constexpr uint32_t kMergeSentinel = 0xffffffffu;
+
+// moved flags of tile `blockIdx.x` as ballot words (mask[i >> 5]) and the tile's moved count
+__global__ void __launch_bounds__(kMergeThreads)
+rebin_flags_kernel(const uint32_t* __restrict__ newk, const uint32_t* __restrict__ oldk, uint32_t n, uint32_t n_old, uint32_t* __restrict__ mask,
+                   uint32_t* __restrict__ tile_moved) {
+  __shared__ uint32_t warp_cnt[kMergeThreads / 32];
+  const uint32_t tile0 = blockIdx.x * (uint32_t)kMergeTile;
+  uint32_t cnt = 0;
+#pragma unroll
+  for (int r = 0; r < kMergeTile / kMergeThreads; ++r) {
+    const uint32_t i = tile0 + r * kMergeThreads + threadIdx.x;
+    const bool moved = i < n && !(i < n_old && newk[i] == oldk[i]);
+    const uint32_t m = __ballot_sync(0xffffffffu, moved);
+    if ((threadIdx.x & 31) == 0) {
+      if (i < n + 32) mask[i >> 5] = m;  // (i is a multiple of 32 here; one word beyond the end stays in bounds: see the allocation)
+      cnt += __popc(m);
+    }
+  }
+  if ((threadIdx.x & 31) == 0) warp_cnt[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int w = 0; w < kMergeThreads / 32; ++w) t += warp_cnt[w];
+    tile_moved[blockIdx.x] = t;
+  }
+}
+
+// single block: exclusive scan of data[0..n) in place, total to *total (and to data[n])
+__global__ void __launch_bounds__(1024) exclusive_scan_total_kernel(uint32_t* data, uint32_t n, uint32_t* total) {
+  __shared__ uint32_t sm[32];
+  uint32_t carry = 0;
+  for (uint32_t base = 0; base < n; base += 1024) {
+    const uint32_t i = base + threadIdx.x;
+    const uint32_t v = (i < n) ? data[i] : 0;
+    uint32_t tot;
+    const uint32_t ex = block_exclusive_scan(v, sm, tot);
+    if (i < n) data[i] = carry + ex;
+    carry += tot;
+  }
+  if (threadIdx.x == 0) {
+    data[n] = carry;
+    *total = carry;
+  }
+}
+
+// per 32-particle word: moved count before it (wprefix); the moved pairs compacted in order (m_up = their
+// number as the host read it back; a larger m_up pads the pair buffers with sentinels that sort last)
+__global__ void __launch_bounds__(kMergeThreads)
+rebin_compact_kernel(const uint32_t* __restrict__ newk, uint32_t n, const uint32_t* __restrict__ mask, const uint32_t* __restrict__ tile_base,
+                     uint32_t* __restrict__ wprefix, uint32_t* __restrict__ mk, uint32_t* __restrict__ mi, uint32_t m_up,
+                     const uint32_t* __restrict__ n_moved_ptr) {
+  constexpr int kWords = kMergeTile / 32;  // 64 ballot words per tile
+  static_assert(kWords == 64, "two warps scan the tile's ballot words");
+  __shared__ uint32_t wpre[kWords];
+  __shared__ uint32_t half_total;
+  const uint32_t tile0 = blockIdx.x * (uint32_t)kMergeTile;
+  const uint32_t n_words = (n + 31) / 32;
+  const uint32_t word0 = tile0 / 32;
+  uint32_t c = 0, inc = 0;
+  if (threadIdx.x < kWords) {  // exclusive prefix of the 64 popcounts: one scan per warp, then the first half's total
+    const uint32_t w = word0 + threadIdx.x;
+    c = (w < n_words) ? __popc(mask[w]) : 0u;
+    inc = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+      if ((threadIdx.x & 31) >= o) inc += t;
+    }
+    if (threadIdx.x == 31) half_total = inc;
+  }
+  __syncthreads();
+  if (threadIdx.x < kWords) wpre[threadIdx.x] = inc - c + (threadIdx.x >= 32 ? half_total : 0u);
+  __syncthreads();
+  const uint32_t base = tile_base[blockIdx.x];
+  if (threadIdx.x < kWords && word0 + threadIdx.x < n_words) wprefix[word0 + threadIdx.x] = base + wpre[threadIdx.x];
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int r = 0; r < kMergeTile / kMergeThreads; ++r) {
+    const uint32_t i = tile0 + r * kMergeThreads + threadIdx.x;
+    if (i >= n) break;
+    const uint32_t m = mask[i >> 5];
+    if ((m >> lane) & 1u) {
+      const uint32_t rank = base + wpre[(i - tile0) >> 5] + __popc(m & ((1u << lane) - 1u));
+      mk[rank] = newk[i];
+      mi[rank] = i;
+    }
+  }
+  const uint32_t n_moved = *n_moved_ptr;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {  // the end marker of the O(1) lookups
+    wprefix[n_words] = n_moved;
+  }
+  for (uint32_t j = n_moved + blockIdx.x * kMergeThreads + threadIdx.x; j < m_up; j += gridDim.x * kMergeThreads) {
+    mk[j] = kMergeSentinel;
+    mi[j] = kMergeSentinel;
+  }
+}
+
+// coarse[q] = sorted_keys[q * kCoarse]
+__global__ void __launch_bounds__(256) coarse_keys_kernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t* __restrict__ coarse) {
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if ((size_t)q * kCoarse < n) coarse[q] = keys[(size_t)q * kCoarse];
+}
+
+__device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* __restrict__ a, uint32_t lo, uint32_t hi, uint32_t v) {
+  while (lo < hi) {
+    const uint32_t mid = lo + ((hi - lo) >> 1);
+    if (a[mid] < v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+// first position of the sorted old keys whose key >= v, through the 1/kCoarse sample
+__device__ __forceinline__ uint32_t lower_bound_two_level(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ coarse, uint32_t n,
+                                                          uint32_t v) {
+  const uint32_t nq = (n + kCoarse - 1) / kCoarse;
+  const uint32_t q = lower_bound_u32(coarse, 0, nq, v);  // first sample >= v: the answer lies in ((q-1) * kCoarse, q * kCoarse]
+  const uint32_t lo = q ? (q - 1) * kCoarse + 1 : 0;
+  const uint32_t hi = min(n, q * (uint32_t)kCoarse);
+  return lower_bound_u32(keys, min(lo, hi), hi, v);
+}
+// moved particles before position p (p in [0, n]) from the ballot words and their prefix counts
+__device__ __forceinline__ uint32_t moved_before(const uint32_t* __restrict__ mask, const uint32_t* __restrict__ wprefix, uint32_t p) {
+  return wprefix[p >> 5] + __popc(mask[p >> 5] & ((1u << (p & 31)) - 1u));
+}
+
+// step 3: final position of every moved pair (sorted by (key, index) in mk / mi)
+__global__ void __launch_bounds__(256)
+rebin_place_moved_kernel(const uint32_t* __restrict__ mk, const uint32_t* __restrict__ mi, uint32_t m_up, const uint32_t* __restrict__ oldk,
+                         const uint32_t* __restrict__ coarse, uint32_t n_old, const uint32_t* __restrict__ mask,
+                         const uint32_t* __restrict__ wprefix, uint32_t* __restrict__ perm, uint32_t* __restrict__ keys_out) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m_up) return;
+  const uint32_t K = mk[j];
+  const uint32_t idx = mi[j];
+  if (K == kMergeSentinel && idx == kMergeSentinel) return;
+  const uint32_t lb = lower_bound_two_level(oldk, coarse, n_old, K);
+  const uint32_t ub = (K == 0xffffffffu) ? n_old : lower_bound_two_level(oldk, coarse, n_old, K + 1u);
+  // stayed particles with this key sit in [lb, ub) of the current order; those before `idx` precede the pair
+  const uint32_t p = idx >= n_old ? ub : min(max(idx, lb), ub);
+  const uint32_t stayed_before = p - moved_before(mask, wprefix, p);
+  const uint32_t pos = j + stayed_before;
+  perm[pos] = idx;
+  keys_out[pos] = K;
+}
+
+// moved pairs below (key, index): pairs compare by key, then by index
+__device__ __forceinline__ uint32_t pairs_below(const uint32_t* __restrict__ k, const uint32_t* __restrict__ ix, uint32_t lo, uint32_t hi, uint32_t key,
+                                                uint32_t index) {
+  while (lo < hi) {
+    const uint32_t mid = lo + ((hi - lo) >> 1);
+    const uint32_t km = k[mid];
+    if (km < key || (km == key && ix[mid] < index)) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// step 4a, one thread per tile: slice_begin[t] = moved pairs below the first stayed particle at or after the
+// start of tile t (n_moved when there is none; also the entry behind the last tile).  Stayed particles have
+// ascending keys, so the pairs a tile's stayed particles can see as their boundary lie in
+// [slice_begin[t], slice_begin[t + 1]].
+__global__ void __launch_bounds__(128)
+rebin_tile_slices_kernel(const uint32_t* __restrict__ newk, uint32_t n, const uint32_t* __restrict__ mask, const uint32_t* __restrict__ mk,
+                         const uint32_t* __restrict__ mi, uint32_t n_moved, uint32_t n_tiles, uint32_t* __restrict__ slice_begin) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t > n_tiles) return;
+  uint32_t first = 0xffffffffu;
+  const uint32_t n_words = (n + 31) / 32;
+  for (uint32_t w = t * (uint32_t)(kMergeTile / 32); w < n_words; ++w) {
+    uint32_t stay = ~mask[w];
+    if (w * 32 + 32 > n) stay &= (1u << (n - w * 32)) - 1u;
+    if (stay) {
+      first = w * 32 + (uint32_t)__ffs(stay) - 1u;
+      break;
+    }
+  }
+  slice_begin[t] = (first == 0xffffffffu) ? n_moved : pairs_below(mk, mi, 0, n_moved, newk[first], first);
+}
+
+// step 4b: final position of every stayed particle of tile `blockIdx.x`
+__global__ void __launch_bounds__(kMergeThreads)
+rebin_place_stayed_kernel(const uint32_t* __restrict__ newk, uint32_t n, const uint32_t* __restrict__ mask, const uint32_t* __restrict__ wprefix,
+                          const uint32_t* __restrict__ mk, const uint32_t* __restrict__ mi, const uint32_t* __restrict__ slice_begin,
+                          uint32_t* __restrict__ perm, uint32_t* __restrict__ keys_out) {
+  constexpr int kWindow = 2048;
+  __shared__ uint32_t wk[kWindow], wi[kWindow];
+  const uint32_t tile0 = blockIdx.x * (uint32_t)kMergeTile;
+  const uint32_t a = slice_begin[blockIdx.x], b = slice_begin[blockIdx.x + 1];
+  const bool staged = (b - a) <= (uint32_t)kWindow;
+  if (staged) {
+    for (uint32_t e = threadIdx.x; e < b - a; e += kMergeThreads) {
+      wk[e] = mk[a + e];
+      wi[e] = mi[a + e];
+    }
+    __syncthreads();
+  }
+  const int lane = threadIdx.x & 31;
+  constexpr int kRounds = kMergeTile / kMergeThreads;
+  uint32_t key[kRounds], m[kRounds], wp[kRounds];
+#pragma unroll
+  for (int r = 0; r < kRounds; ++r) {  // all loads first: the searches below then overlap
+    const uint32_t i = tile0 + r * kMergeThreads + threadIdx.x;
+    const bool in = i < n;
+    key[r] = in ? newk[i] : 0u;
+    m[r] = in ? mask[i >> 5] : 0xffffffffu;
+    wp[r] = in ? wprefix[i >> 5] : 0u;
+  }
+  if (staged) {
+    const uint32_t len = b - a;
+    uint32_t lo[kRounds], hi[kRounds];
+#pragma unroll
+    for (int r = 0; r < kRounds; ++r) lo[r] = 0, hi[r] = len;
+    // the eight searches of a thread advance together (branch-free steps; len <= 2048: at most 12 of them)
+    for (uint32_t span = len; span; span >>= 1) {
+#pragma unroll
+      for (int r = 0; r < kRounds; ++r) {
+        const uint32_t i = tile0 + r * kMergeThreads + threadIdx.x;
+        if (lo[r] < hi[r]) {
+          const uint32_t mid = lo[r] + ((hi[r] - lo[r]) >> 1);
+          const uint32_t km = wk[mid];
+          const bool below = km < key[r] || (km == key[r] && wi[mid] < i);
+          lo[r] = below ? mid + 1 : lo[r];
+          hi[r] = below ? hi[r] : mid;
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < kRounds; ++r) {
+      const uint32_t i = tile0 + r * kMergeThreads + threadIdx.x;
+      if ((m[r] >> lane) & 1u) continue;  // moved (or beyond the end): placed by rebin_place_moved_kernel
+      const uint32_t pos = (i - (wp[r] + __popc(m[r] & ((1u << lane) - 1u)))) + a + lo[r];
+      perm[pos] = i;
+      keys_out[pos] = key[r];
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < kRounds; ++r) {
+      const uint32_t i = tile0 + r * kMergeThreads + threadIdx.x;
+      if ((m[r] >> lane) & 1u) continue;
+      const uint32_t pos = (i - (wp[r] + __popc(m[r] & ((1u << lane) - 1u)))) + pairs_below(mk, mi, a, b, key[r], i);
+      perm[pos] = i;
+      keys_out[pos] = key[r];
+    }
+  }
+}
+
 // out[0] = first sorted position whose key >= key_lo, out[1] = first whose key >= key_hi (slab handles:
 // the particles before out[0] / from out[1] on can reach the planes shared with a neighbour)
 __global__ void split_bounds_kernel(const uint32_t* __restrict__ keys, uint32_t count, uint32_t key_lo, uint32_t key_hi,
