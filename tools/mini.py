@@ -1,22 +1,40 @@
-"""Tiny end-to-end run for compute-sanitizer: python tools/mini.py [N] [particles] [steps] [fuse]"""
-import sys, os
+"""Small end-to-end run that touches every kernel of the library, for compute-sanitizer:
+    compute-sanitizer --tool memcheck python tools/mini.py        (also racecheck / initcheck / synccheck)
+Every model in both arithmetic policies, the hand-over and the classic pipeline, the staged and the generic
+kernels, radix and merge re-bins, the stale-order P2G variant, graph replay, the on-device generator."""
+import os
+import sys
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
+
 import mpm_b200
+
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 P = int(sys.argv[2]) if len(sys.argv) > 2 else 20000
-steps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
-fuse = int(sys.argv[4]) if len(sys.argv) > 4 else 0
-for model in (mpm_b200.FIXED_COROTATED, mpm_b200.SNOW):
-    mats = mpm_b200.make_material(0.512 / P, 1000.0, 1.4e5, 0.2, 0.0, 0.0, 1e30)
-    sim = mpm_b200.Sim(N, 1e-4, mats, model=model, svd_mode=mpm_b200.SVD_FAST, sort_every=2, fuse_mode=fuse, capacity=2 * P)
-    sim.generate_dense_block(P, seed=1)
-    sim.advance(steps)
-    d = sim.download()
-    sim.append(np.ascontiguousarray(d[: P // 4]))   # an object entering
-    sim.advance(steps)
-    x = sim.download_positions()
-    sim.sync()
-    d = sim.download()
-    print("ok", model, fuse, len(d), float(d["v"][:, 1].mean()), float(x.mean()))
+steps = int(sys.argv[3]) if len(sys.argv) > 3 else 6
+
+
+def run(model, svd, pipeline, p2g_mode, g2p_mode, graph_mode, shear):
+    mats = mpm_b200.make_material(0.512 / P, 1000.0, 1.4e5, 0.2, 10.0, 0.975, 1.0075)
+    sim = mpm_b200.Sim(N, 1e-4, mats, model=model, svd_mode=svd, sort_every=2, capacity=2 * P, pipeline=pipeline,
+                       p2g_mode=p2g_mode, g2p_mode=g2p_mode, graph_mode=graph_mode)
+    sim.generate_dense_block(P, seed=7, shear=shear, f_noise=0.03 if shear else 0.0)
+    for _ in range(3):
+        sim.advance(steps)
+    got = sim.download()
+    d = sim.diagnostics()
+    assert np.isfinite(got["x"]).all() and d["nonfinite"] == 0, d
+    out = (sim.launches, sim.rebins, sim.merge_rebins, sim.graph_replays)
     sim.close()
+    return out
+
+
+for model in (mpm_b200.FIXED_COROTATED, mpm_b200.SNOW, mpm_b200.JELLY):
+    for svd in (mpm_b200.SVD_EXACT, mpm_b200.SVD_FAST):
+        for pipeline in (mpm_b200.PIPE_HANDOVER, mpm_b200.PIPE_CLASSIC):
+            print(model, svd, pipeline, run(model, svd, pipeline, mpm_b200.P2G_RUNS, mpm_b200.G2P_TILE, mpm_b200.GRAPH_OFF, 0.0))
+print("sheared", run(mpm_b200.SNOW, mpm_b200.SVD_FAST, mpm_b200.PIPE_HANDOVER, mpm_b200.P2G_RUNS, mpm_b200.G2P_TILE, mpm_b200.GRAPH_OFF, 200.0))
+print("graphs", run(mpm_b200.SNOW, mpm_b200.SVD_FAST, mpm_b200.PIPE_HANDOVER, mpm_b200.P2G_RUNS, mpm_b200.G2P_TILE, mpm_b200.GRAPH_ON, 0.0))
+print("generic", run(mpm_b200.SNOW, mpm_b200.SVD_EXACT, mpm_b200.PIPE_CLASSIC, mpm_b200.P2G_DIRECT, mpm_b200.G2P_DIRECT, mpm_b200.GRAPH_OFF, 0.0))
+print("mini ok")
