@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define MPM_B200_ABI_VERSION 5
+#define MPM_B200_ABI_VERSION 6
 
 /* which MaterialModel alias the kernels are instantiated for (reference include/mpm.cuh:25): the classes of
  * include/mpm_b200/MaterialModel.cuh.  Ids >= MPM_MODEL_USER are materials compiled in through
@@ -131,6 +131,22 @@ int mpm_upload_particles_with_ids(MpmSim* sim, const MpmParticle* particles, con
 int mpm_append_particles_aos(MpmSim* sim, const MpmParticle* particles, size_t count);
 /* particlesToHost (src/mpm.cu:288-306): blocking; particles come back in upload order */
 int mpm_download_particles_aos(MpmSim* sim, MpmParticle* particles, size_t capacity, size_t* count);
+/* Overlapped transfers for loops that stream particle sets through one handle (whole-domain handles, pinned
+ * host memory).  The reference copies and computes strictly in turn (particlesToDevice / advance /
+ * particlesToHost on the default stream, src/mpm.cu:278-306); these keep its data formats and overlap the
+ * PCIe copies of one particle set with the substeps of another:
+ *   mpm_prefetch_particles_aos        starts the host -> device copy of `particles` into a second staging buffer
+ *                                     on a copy stream and returns.  A later mpm_upload_particles_aos of the SAME
+ *                                     pointer and count uses that copy (and waits for it on the device) instead
+ *                                     of copying again; any other upload ignores it.  The host buffer must stay
+ *                                     unchanged until that upload.
+ *   mpm_download_particles_aos_async  like mpm_download_particles_aos, but the device -> host copy runs on a copy
+ *                                     stream and the call returns; substeps and uploads issued afterwards overlap
+ *                                     it.  `particles` is valid after mpm_download_wait.  One read-back in
+ *                                     flight at a time: a second one queues behind the first. */
+int mpm_prefetch_particles_aos(MpmSim* sim, const MpmParticle* particles, size_t count);
+int mpm_download_particles_aos_async(MpmSim* sim, MpmParticle* particles, size_t capacity, size_t* count);
+int mpm_download_wait(MpmSim* sim);
 /* positions only (12 B/particle), upload order — what the reference's viewer cadence needs */
 int mpm_download_positions(MpmSim* sim, float* xyz, size_t capacity, size_t* count);
 /* the same without blocking: the copy is queued behind the substeps issued so far and overlaps the

@@ -82,6 +82,9 @@ def lib():
         L.mpm_append_particles_aos.argtypes = [_vp, _vp, ctypes.c_size_t]
         L.mpm_upload_particles_with_ids.argtypes = [_vp, _vp, _vp, ctypes.c_size_t]
         L.mpm_download_particles_aos.argtypes = [_vp, _vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
+        L.mpm_prefetch_particles_aos.argtypes = [_vp, _vp, ctypes.c_size_t]
+        L.mpm_download_particles_aos_async.argtypes = [_vp, _vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
+        L.mpm_download_wait.argtypes = [_vp]
         L.mpm_download_positions.argtypes = [_vp, _vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
         L.mpm_download_positions_async.argtypes = [_vp, _vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
         L.mpm_generate_dense_block.argtypes = [_vp, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_float,
@@ -189,6 +192,19 @@ class Sim:
         cnt = ctypes.c_size_t()
         self._ck(lib().mpm_download_particles_aos(self._h, _vp(ptr), capacity, ctypes.byref(cnt)))
         return cnt.value
+
+    def prefetch_ptr(self, ptr, count):
+        """Starts the host -> device copy of a pinned AoS buffer; a later upload_ptr of the same buffer uses it."""
+        self._ck(lib().mpm_prefetch_particles_aos(self._h, _vp(ptr), count))
+
+    def download_ptr_async(self, ptr, capacity):
+        """Queues the read-back into a pinned AoS buffer; valid after download_wait()."""
+        cnt = ctypes.c_size_t()
+        self._ck(lib().mpm_download_particles_aos_async(self._h, _vp(ptr), capacity, ctypes.byref(cnt)))
+        return cnt.value
+
+    def download_wait(self):
+        self._ck(lib().mpm_download_wait(self._h))
 
     def download_positions(self):
         out = np.empty((self.count, 3), np.float32)

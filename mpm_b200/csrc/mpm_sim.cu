@@ -114,6 +114,16 @@ struct MpmSim {
 
   MpmParticle* aos_stage = nullptr;  // device AoS staging for upload/download
   size_t aos_stage_cap = 0;
+  // overlapped transfers (mpm_prefetch_particles_aos / mpm_download_particles_aos_async): a second staging
+  // buffer filled by its own copy stream while the substeps run, and the read-back of aos_stage on another
+  MpmParticle* aos_prefetch = nullptr;
+  size_t aos_prefetch_cap = 0;
+  const MpmParticle* prefetched_ptr = nullptr;  // host buffer whose copy sits in (or is on its way to) aos_prefetch
+  size_t prefetched_count = 0;
+  cudaStream_t io_in = nullptr, io_out = nullptr;
+  cudaEvent_t ev_prefetched = nullptr, ev_consumed = nullptr, ev_staged = nullptr, ev_downloaded = nullptr;
+  bool prefetch_consumed_recorded = false;
+  bool download_pending = false;
   unsigned long long* d_counter = nullptr;
   DeviceDiag* d_diag = nullptr;
   DeviceDiag* h_diag = nullptr;  // pinned
@@ -246,8 +256,12 @@ int ensure_capacity(MpmSim* sim, size_t cap) {
   return 0;
 }
 
+// the AoS staging buffer for n records; whatever the caller queues on sim->stream next runs after a pending
+// asynchronous read-back of the buffer (mpm_download_particles_aos_async)
 int ensure_stage(MpmSim* sim, size_t n) {
+  if (sim->download_pending) CK(cudaStreamWaitEvent(sim->stream, sim->ev_downloaded, 0));
   if (n <= sim->aos_stage_cap) return 0;
+  if (sim->download_pending) CK(cudaEventSynchronize(sim->ev_downloaded));
   cudaFree(sim->aos_stage);
   sim->aos_stage = nullptr;
   sim->aos_stage_cap = 0;
@@ -744,7 +758,14 @@ void mpm_destroy(MpmSim* sim) {
   cudaFree(sim->grid);
   cudaFree(sim->mats_dev);
   free(sim->mats_host);
+  if (sim->io_in) cudaStreamSynchronize(sim->io_in);
+  if (sim->io_out) cudaStreamSynchronize(sim->io_out);
   cudaFree(sim->aos_stage);
+  cudaFree(sim->aos_prefetch);
+  for (cudaEvent_t e : {sim->ev_prefetched, sim->ev_consumed, sim->ev_staged, sim->ev_downloaded})
+    if (e) cudaEventDestroy(e);
+  if (sim->io_in) cudaStreamDestroy(sim->io_in);
+  if (sim->io_out) cudaStreamDestroy(sim->io_out);
   cudaFree(sim->d_counter);
   cudaFree(sim->d_diag);
   cudaFree(sim->d_moved);
@@ -771,13 +792,23 @@ static int upload_impl(MpmSim* sim, const MpmParticle* particles, size_t count, 
   drop_graphs(sim);
   CK(cudaSetDevice(sim->device));
   if (int rc = ensure_capacity(sim, std::max<size_t>(count, 1))) return rc;
-  if (int rc = ensure_stage(sim, std::max<size_t>(count, 1))) return rc;
+  // the records are already on the device (or on their way) if this buffer was announced with mpm_prefetch_particles_aos
+  const bool prefetched = count && particles == sim->prefetched_ptr && count == sim->prefetched_count && !sim->comm.active() && !ids;
+  sim->prefetched_ptr = nullptr;
+  if (!prefetched)  // (the prefetched path does not touch the staging buffer, which a read-back may still be using)
+    if (int rc = ensure_stage(sim, std::max<size_t>(count, 1))) return rc;
   sim->count = count;
   sim->first_id = 0;
   sim->cur = 0;
   sim->form_ad = false;
   CK(cudaMemsetAsync(&sim->d_diag->jp_not_one, 0, sizeof(unsigned int), sim->stream));
-  if (count) CK(cudaMemcpyAsync(sim->aos_stage, particles, sizeof(MpmParticle) * count, cudaMemcpyHostToDevice, sim->stream));
+  const MpmParticle* records = sim->aos_stage;
+  if (prefetched) {
+    CK(cudaStreamWaitEvent(sim->stream, sim->ev_prefetched, 0));
+    records = sim->aos_prefetch;
+  } else if (count) {
+    CK(cudaMemcpyAsync(sim->aos_stage, particles, sizeof(MpmParticle) * count, cudaMemcpyHostToDevice, sim->stream));
+  }
   if (count && !sim->comm.active() && !ids) {
     // the common path: keys from the records, sort the (key, index) pairs, then ONE pass that gathers the
     // records in cell order and writes the SoA — the particles never travel through the SoA unsorted
@@ -787,11 +818,15 @@ static int upload_impl(MpmSim* sim, const MpmParticle* particles, size_t count, 
     sim->moved_seen = 0;
     sim->moved_pending = false;
     CK(cudaMemsetAsync(sim->d_moved, 0, sizeof(unsigned long long), sim->stream));
-    aos_keys_kernel<<<blocks_for(count, 256), 256, 0, sim->stream>>>(sim->aos_stage, count, sim->k, sim->keys[0], sim->vals[0], sim->d_diag);
+    aos_keys_kernel<<<blocks_for(count, 256), 256, 0, sim->stream>>>(records, count, sim->k, sim->keys[0], sim->vals[0], sim->d_diag);
     const uint32_t* perm = sort_pairs(sim, count);
-    aos_gather_to_soa_kernel<<<blocks_for(count, kTile), kTile, 0, sim->stream>>>(sim->aos_stage, perm, sim->soa[0], count, 0);
+    aos_gather_to_soa_kernel<<<blocks_for(count, kTile), kTile, 0, sim->stream>>>(records, perm, sim->soa[0], count, 0);
     sim->launches += 2;
     CK(cudaGetLastError());
+    if (prefetched) {  // the next prefetch may overwrite the buffer from here on
+      CK(cudaEventRecord(sim->ev_consumed, sim->stream));
+      sim->prefetch_consumed_recorded = true;
+    }
     return 0;
   }
   if (count) {
@@ -843,6 +878,66 @@ int mpm_download_particles_aos(MpmSim* sim, MpmParticle* particles, size_t capac
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(particles, sim->aos_stage, sizeof(MpmParticle) * sim->count, cudaMemcpyDeviceToHost, sim->stream));
   CK(cudaStreamSynchronize(sim->stream));
+  return 0;
+}
+
+static int io_objects(MpmSim* sim) {
+  if (sim->io_in) return 0;
+  CK(cudaStreamCreateWithFlags(&sim->io_in, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&sim->io_out, cudaStreamNonBlocking));
+  for (cudaEvent_t* e : {&sim->ev_prefetched, &sim->ev_consumed, &sim->ev_staged, &sim->ev_downloaded})
+    CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  return 0;
+}
+
+int mpm_prefetch_particles_aos(MpmSim* sim, const MpmParticle* particles, size_t count) {
+  if (!sim || !particles || count == 0) return fail(sim, "mpm_prefetch_particles_aos: null argument");
+  CK(cudaSetDevice(sim->device));
+  if (!sim->whole_domain) return fail(sim, "mpm_prefetch_particles_aos: not for slab handles");
+  if (int rc = io_objects(sim)) return rc;
+  if (count > sim->aos_prefetch_cap) {
+    CK(cudaStreamSynchronize(sim->io_in));
+    if (sim->prefetch_consumed_recorded) CK(cudaEventSynchronize(sim->ev_consumed));
+    cudaFree(sim->aos_prefetch);
+    sim->aos_prefetch = nullptr;
+    sim->aos_prefetch_cap = 0;
+    CK(cudaMalloc(&sim->aos_prefetch, sizeof(MpmParticle) * count));
+    sim->aos_prefetch_cap = count;
+  }
+  // an upload that still reads the previous contents goes first
+  if (sim->prefetch_consumed_recorded) CK(cudaStreamWaitEvent(sim->io_in, sim->ev_consumed, 0));
+  CK(cudaMemcpyAsync(sim->aos_prefetch, particles, sizeof(MpmParticle) * count, cudaMemcpyHostToDevice, sim->io_in));
+  CK(cudaEventRecord(sim->ev_prefetched, sim->io_in));
+  sim->prefetched_ptr = particles;
+  sim->prefetched_count = count;
+  return 0;
+}
+
+int mpm_download_particles_aos_async(MpmSim* sim, MpmParticle* particles, size_t capacity, size_t* count) {
+  if (!sim) return 1;
+  CK(cudaSetDevice(sim->device));
+  if (count) *count = sim->count;
+  if (capacity < sim->count) return fail(sim, "mpm_download_particles_aos_async: capacity %zu < %zu", capacity, sim->count);
+  if (sim->count == 0) return 0;
+  if (int rc = io_objects(sim)) return rc;
+  if (int rc = ensure_stage(sim, sim->count)) return rc;  // (also orders this conversion behind a read-back still in flight)
+  soa_to_aos_kernel<<<blocks_for(sim->count, kTile), kTile, 0, sim->stream>>>(sim->soa[sim->cur], sim->count, sim->aos_stage, sim->first_id, sim->whole_domain);
+  sim->launches++;
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(sim->ev_staged, sim->stream));
+  CK(cudaStreamWaitEvent(sim->io_out, sim->ev_staged, 0));
+  CK(cudaMemcpyAsync(particles, sim->aos_stage, sizeof(MpmParticle) * sim->count, cudaMemcpyDeviceToHost, sim->io_out));
+  CK(cudaEventRecord(sim->ev_downloaded, sim->io_out));
+  sim->download_pending = true;
+  return 0;
+}
+
+int mpm_download_wait(MpmSim* sim) {
+  if (!sim) return 1;
+  if (!sim->download_pending) return 0;
+  CK(cudaSetDevice(sim->device));
+  CK(cudaEventSynchronize(sim->ev_downloaded));
+  sim->download_pending = false;
   return 0;
 }
 

@@ -22,7 +22,7 @@ def test_every_declared_symbol_is_exported():
     assert len(names) >= 25
     for n in names:
         assert hasattr(L, n), n
-    assert L.mpm_abi_version() == 5
+    assert L.mpm_abi_version() == 6
 
 
 def test_layouts_match_reference_sizes():

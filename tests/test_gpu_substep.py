@@ -374,6 +374,59 @@ def test_positions_readback_blocking_and_async():
     assert np.array_equal(sim.download_positions(), sim.download()["x"])
 
 
+def test_overlapped_transfers_give_the_blocking_results():
+    """mpm_prefetch_particles_aos / mpm_download_particles_aos_async: particle sets streamed through one handle
+    with the copies of one set overlapping the substeps of another give what the blocking calls give."""
+    import torch
+
+    N, steps, n_sets = 32, 6, 4
+    base, mats = scenes.two_spheres(N)
+    n = len(base)
+    sets = []
+    for k in range(n_sets):
+        q = base.copy()
+        q["v"][:, 1] += 0.25 * k          # different inputs, so that a stale buffer would show
+        sets.append(q)
+
+    def pinned(src=None):
+        t = torch.empty(n * 104, dtype=torch.uint8, pin_memory=True)
+        a = t.numpy().view(ol.PARTICLE_DTYPE)
+        if src is not None:
+            a[:] = src
+        return t, a
+
+    want = []
+    sim = _sim(N, mats, ol.SNOW, sort_every=2)
+    for q in sets:
+        sim.upload(q)
+        sim.advance(steps)
+        want.append(sim.download())
+    sim.close()
+
+    ins = [pinned(q) for q in sets]
+    outs = [pinned() for _ in sets]
+    sim = _sim(N, mats, ol.SNOW, sort_every=2)
+    sim.prefetch_ptr(ins[0][0].data_ptr(), n)
+    for k in range(n_sets):
+        sim.upload_ptr(ins[k][0].data_ptr(), n)                   # consumes the prefetched copy
+        if k + 1 < n_sets:
+            sim.prefetch_ptr(ins[k + 1][0].data_ptr(), n)          # travels while set k is simulated
+        sim.advance(steps)
+        assert sim.download_ptr_async(outs[k][0].data_ptr(), n) == n   # travels while set k + 1 is simulated
+    sim.download_wait()
+    for k in range(n_sets):
+        for f in ("x", "v", "F", "C", "Jp"):   # (not bit for bit: the order of P2G's float reductions differs from run to run)
+            assert np.allclose(outs[k][1][f], want[k][f], rtol=0, atol=2e-4 if f == "C" else 2e-5), (k, f)
+    # a prefetch that no upload takes up is harmless, as is an upload of another buffer in between
+    sim.prefetch_ptr(ins[1][0].data_ptr(), n)
+    sim.upload(sets[2])
+    sim.advance(steps)
+    got = sim.download()
+    for f in ("x", "v", "F", "C", "Jp"):
+        assert np.allclose(got[f], want[2][f], rtol=0, atol=2e-4 if f == "C" else 2e-5), f
+    sim.close()
+
+
 def test_free_fall_velocity():
     """Oracle-free invariant: before contact v_y(t) = -9.81 t (SURVEY.md 8(c) pin 6)."""
     N = 32
