@@ -76,59 +76,101 @@ def workload(gpus, scaling="weak"):
 
 
 class ClockSampler:
-    """nvidia-smi clocks during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons during the timed region (B200_PROFILING.md recipe), sampled every 5 ms through
+    NVML in a thread (a timed region of ~0.2 s falls between two lines of `nvidia-smi -lms`, whose queries take
+    longer than that); nvidia-smi is the fallback when NVML cannot be loaded."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         self.index = index
-        self.rows = []
+        self.rows = []      # (t, sm_mhz, sm_max_mhz, [reason names])
         self.proc = None
+        self.nvml = None
+        self.running = False
+        self.source = None
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[self.index])
+            except Exception:
+                pass
+        return self.index
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.running = True
+            self.source = "nvml"
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self._physical_index()), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        bits = {"hw_slowdown": getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while self.running:
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.rows.append((time.monotonic(), sm, self.smax, [k for k, b in bits.items() if mask & b]))
+            except Exception:
+                pass
+            time.sleep(0.005)
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append((time.monotonic(), [c.strip() for c in line.split(",")]))
+            c = [x.strip() for x in line.split(",")]
+            try:
+                self.rows.append((time.monotonic(), float(c[1]), float(c[2]),
+                                  [n for n, v in zip(self.NAMES, c[5:9]) if v.lower().startswith("active")]))
+            except Exception:
+                pass
 
     def stop(self, t0=None, t1=None):
         """Samples taken inside [t0, t1] (host monotonic clock around the timed region); the sampler is
-        started before the warm-up so that nvidia-smi is already streaming when the region begins."""
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        started before the warm-up so that it is already streaming when the region begins."""
+        if not self.nvml and not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML, no nvidia-smi"]}
         time.sleep(0.05)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, smax, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        inside = [r for (t, r) in self.rows if t0 is None or (t0 <= t <= t1 + 0.03)]
+        self.running = False
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        inside = [r for r in self.rows if t0 is None or (t0 <= r[0] <= t1)]
         window = "timed region"
         if not inside:  # a very short region can fall between two samples: use the ones around it
-            inside = [r for (t, r) in self.rows if t0 is None or (t0 - 0.5 <= t <= t1 + 0.5)]
+            inside = [r for r in self.rows if t0 is None or (t0 - 0.5 <= r[0] <= t1 + 0.5)]
             window = "timed region +- 0.5 s (none fell inside)"
-        for r in inside:
-            try:
-                sm.append(float(r[1]))
-                smax.append(float(r[2]))
-                for n, v in zip(names, r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
-            except Exception:
-                pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm), "window": window}
+        sm = [r[1] for r in inside]
+        reasons = sorted({n for r in inside for n in r[3]})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(r[2] for r in inside) if inside else None,
+                "reasons": reasons, "samples": len(sm), "window": window, "source": self.source}
 
 
 # --------------------------------------------------------------------------------------------------
