@@ -131,8 +131,7 @@ int mpm_upload_particles_with_ids(MpmSim* sim, const MpmParticle* particles, con
 int mpm_append_particles_aos(MpmSim* sim, const MpmParticle* particles, size_t count);
 /* particlesToHost (src/mpm.cu:288-306): blocking; particles come back in upload order */
 int mpm_download_particles_aos(MpmSim* sim, MpmParticle* particles, size_t capacity, size_t* count);
-/* Overlapped transfers for loops that stream particle sets through one handle (whole-domain handles, pinned
- * host memory).  The reference copies and computes strictly in turn (particlesToDevice / advance /
+/* Overlapped transfers for loops that stream particle sets through one handle (pinned host memory).  The reference copies and computes strictly in turn (particlesToDevice / advance /
  * particlesToHost on the default stream, src/mpm.cu:278-306); these keep its data formats and overlap the
  * PCIe copies of one particle set with the substeps of another:
  *   mpm_prefetch_particles_aos        starts the host -> device copy of `particles` into a second staging buffer

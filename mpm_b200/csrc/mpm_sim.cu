@@ -793,7 +793,7 @@ static int upload_impl(MpmSim* sim, const MpmParticle* particles, size_t count, 
   CK(cudaSetDevice(sim->device));
   if (int rc = ensure_capacity(sim, std::max<size_t>(count, 1))) return rc;
   // the records are already on the device (or on their way) if this buffer was announced with mpm_prefetch_particles_aos
-  const bool prefetched = count && particles == sim->prefetched_ptr && count == sim->prefetched_count && !sim->comm.active() && !ids;
+  const bool prefetched = count && particles == sim->prefetched_ptr && count == sim->prefetched_count && !ids;
   sim->prefetched_ptr = nullptr;
   if (!prefetched)  // (the prefetched path does not touch the staging buffer, which a read-back may still be using)
     if (int rc = ensure_stage(sim, std::max<size_t>(count, 1))) return rc;
@@ -830,9 +830,13 @@ static int upload_impl(MpmSim* sim, const MpmParticle* particles, size_t count, 
     return 0;
   }
   if (count) {
-    aos_to_soa_kernel<<<blocks_for(count, 256), 256, 0, sim->stream>>>(sim->aos_stage, sim->soa[0], count, 0, 0, sim->d_diag);
+    aos_to_soa_kernel<<<blocks_for(count, 256), 256, 0, sim->stream>>>(records, sim->soa[0], count, 0, 0, sim->d_diag);
     sim->launches++;
     CK(cudaGetLastError());
+    if (prefetched) {
+      CK(cudaEventRecord(sim->ev_consumed, sim->stream));
+      sim->prefetch_consumed_recorded = true;
+    }
     if (ids) CK(cudaMemcpyAsync(sim->soa[0].id, ids, sizeof(uint32_t) * count, cudaMemcpyHostToDevice, sim->stream));
   }
   // bin immediately: the substep kernels assume cell-sorted order for locality
@@ -893,7 +897,6 @@ static int io_objects(MpmSim* sim) {
 int mpm_prefetch_particles_aos(MpmSim* sim, const MpmParticle* particles, size_t count) {
   if (!sim || !particles || count == 0) return fail(sim, "mpm_prefetch_particles_aos: null argument");
   CK(cudaSetDevice(sim->device));
-  if (!sim->whole_domain) return fail(sim, "mpm_prefetch_particles_aos: not for slab handles");
   if (int rc = io_objects(sim)) return rc;
   if (count > sim->aos_prefetch_cap) {
     CK(cudaStreamSynchronize(sim->io_in));
