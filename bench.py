@@ -531,7 +531,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--emulate-rank", default=None, metavar="R/W",
                     help="experiments on one GPU: the slab geometry (N, planes, particle share) of rank R of W, without neighbours; "
-                         "use with MPM_BENCH_NO_CHECKS=1 --no-extras --no-e2e")
+                         "use with --no-extras --no-e2e (the invariants are not checked: the slab has no neighbours to exchange with)")
     ap.add_argument("--no-extras", action="store_true", help="skip the extra configurations / stressed workloads / N-rank parity")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -548,8 +548,7 @@ def main():
     sim.generate_dense_block(P_total, seed=1234, shear=args.shear, f_noise=args.f_noise)
     sim.sync()
     P_local, G_local = sim.count, sim.grid_nodes
-    # (MPM_BENCH_NO_CHECKS: timing experiments with kernels that compute garbage on purpose, tools/ab.py)
-    inv = None if os.environ.get("MPM_BENCH_NO_CHECKS") else invariants(ctx, sim, P_total, mass, slabs[rank], N)
+    inv = None if args.emulate_rank else invariants(ctx, sim, P_total, mass, slabs[rank], N)
 
     sampler = ClockSampler(ctx.local_rank)
     if rank == 0:

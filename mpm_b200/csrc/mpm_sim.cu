@@ -529,7 +529,7 @@ int do_p2g_and_exchange(MpmSim* sim, bool keys, bool* keys_done) {
     sim->split_pending = false;
     sim->split_valid = true;
   }
-  const bool overlap = sim->split_valid && !sim->timing && getenv("MPM_NO_OVERLAP") == nullptr;
+  const bool overlap = sim->split_valid && !sim->timing;
   if (!overlap) {
     {
       StageTimer tm(sim, MPM_STAGE_P2G);
