@@ -129,6 +129,11 @@ int mpm_upload_particles_with_ids(MpmSim* sim, const MpmParticle* particles, con
  * the reference re-uploads everything from stale host copies, src/mpm.cu:298-314).  Their ids continue
  * the upload order.  Needs room: set MpmParams.capacity to the total over all objects. */
 int mpm_append_particles_aos(MpmSim* sim, const MpmParticle* particles, size_t count);
+/* removes the particles at positions [first, first + count) of the upload order (an object whose lifetime ends,
+ * include/mpm.cuh:36-40; the reference rebuilds its device arrays from host copies, src/mpm.cu:298-314).  On
+ * the device: a stable compaction that keeps the cell order; the particles behind the range move up in the
+ * upload order, so later downloads return the survivors contiguously.  Whole-domain handles only. */
+int mpm_remove_particles(MpmSim* sim, size_t first, size_t count);
 /* particlesToHost (src/mpm.cu:288-306): blocking; particles come back in upload order */
 int mpm_download_particles_aos(MpmSim* sim, MpmParticle* particles, size_t capacity, size_t* count);
 /* Overlapped transfers for loops that stream particle sets through one handle (pinned host memory).  The reference copies and computes strictly in turn (particlesToDevice / advance /

@@ -82,6 +82,7 @@ def lib():
         L.mpm_append_particles_aos.argtypes = [_vp, _vp, ctypes.c_size_t]
         L.mpm_upload_particles_with_ids.argtypes = [_vp, _vp, _vp, ctypes.c_size_t]
         L.mpm_download_particles_aos.argtypes = [_vp, _vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
+        L.mpm_remove_particles.argtypes = [_vp, ctypes.c_size_t, ctypes.c_size_t]
         L.mpm_prefetch_particles_aos.argtypes = [_vp, _vp, ctypes.c_size_t]
         L.mpm_download_particles_aos_async.argtypes = [_vp, _vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
         L.mpm_download_wait.argtypes = [_vp]
@@ -166,6 +167,10 @@ class Sim:
         """More particles into the active set (an object whose lifetime begins); ids continue."""
         assert particles.dtype == PARTICLE_DTYPE and particles.flags.c_contiguous
         self._ck(lib().mpm_append_particles_aos(self._h, _ptr(particles), particles.shape[0]))
+
+    def remove(self, first, count):
+        """Drops the particles at positions [first, first + count) of the upload order (an object whose lifetime ends)."""
+        self._ck(lib().mpm_remove_particles(self._h, first, count))
 
     def overwrite(self, particles):
         """New particle data (upload order) into the existing slots, without re-binning."""

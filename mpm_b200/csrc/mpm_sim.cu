@@ -870,6 +870,38 @@ int mpm_append_particles_aos(MpmSim* sim, const MpmParticle* particles, size_t c
   return do_sort(sim);
 }
 
+int mpm_remove_particles(MpmSim* sim, size_t first, size_t count) {
+  if (!sim) return 1;
+  CK(cudaSetDevice(sim->device));
+  if (!sim->whole_domain) return fail(sim, "mpm_remove_particles: not for slab handles");
+  if (first + count > sim->count) return fail(sim, "mpm_remove_particles: [%zu, %zu) is not a range of the %zu particles", first, first + count, sim->count);
+  if (count == 0) return 0;
+  drop_graphs(sim);
+  const size_t n = sim->count;
+  if (count == n) {
+    sim->count = 0;
+    sim->okeys_count = 0;
+    return 0;
+  }
+  const uint32_t id0 = sim->first_id + (uint32_t)first, id1 = id0 + (uint32_t)count;
+  const unsigned n_tiles = blocks_for(n, kMergeTile);
+  Soa& src = sim->soa[sim->cur];
+  Soa& dst = sim->soa[sim->cur ^ 1];
+  uint32_t* perm = sim->vals[1];
+  remove_flags_kernel<<<n_tiles, kMergeThreads, 0, sim->stream>>>(src.id, (uint32_t)n, id0, id1, sim->mmask, sim->tile_moved);
+  exclusive_scan_total_kernel<<<1, 1024, 0, sim->stream>>>(sim->tile_moved, n_tiles, sim->d_n_moved);
+  remove_perm_kernel<<<n_tiles, kMergeThreads, 0, sim->stream>>>((uint32_t)n, sim->mmask, sim->tile_moved, perm);
+  const size_t left = n - count;
+  permute_kernel<false><<<blocks_for(left, 256), 256, 0, sim->stream>>>(src, dst, perm, left, sim->k);
+  renumber_ids_kernel<<<blocks_for(left, 256), 256, 0, sim->stream>>>(dst.id, (uint32_t)left, id1, (uint32_t)count);
+  sim->launches += 5;
+  CK(cudaGetLastError());
+  sim->cur ^= 1;
+  sim->count = left;
+  sim->okeys_count = 0;  // the keys of the last re-bin no longer line up with the slots: the next re-bin sorts in full
+  return 0;
+}
+
 int mpm_download_particles_aos(MpmSim* sim, MpmParticle* particles, size_t capacity, size_t* count) {
   if (!sim) return 1;
   CK(cudaSetDevice(sim->device));

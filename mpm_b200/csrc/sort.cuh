@@ -508,6 +508,67 @@ rebin_place_stayed_kernel(const uint32_t* __restrict__ newk, uint32_t n, const u
   }
 }
 
+// ---- removal of an id range (an object whose lifetime ends, include/mpm.cuh:36-40) ------------------------
+// Stable compaction of the survivors: the order within the survivors — the cell order — is kept, so no
+// re-bin is needed afterwards.  Same building blocks as the merge re-bin: ballot words of the REMOVED
+// particles, their per-tile counts, an exclusive scan, then perm[rank among survivors] = slot.
+__global__ void __launch_bounds__(kMergeThreads)
+remove_flags_kernel(const uint32_t* __restrict__ ids, uint32_t n, uint32_t id_begin, uint32_t id_end, uint32_t* __restrict__ mask,
+                    uint32_t* __restrict__ tile_removed) {
+  __shared__ uint32_t warp_cnt[kMergeThreads / 32];
+  const uint32_t tile0 = blockIdx.x * (uint32_t)kMergeTile;
+  uint32_t cnt = 0;
+#pragma unroll
+  for (int r = 0; r < kMergeTile / kMergeThreads; ++r) {
+    const uint32_t i = tile0 + r * kMergeThreads + threadIdx.x;
+    const bool removed = i < n && ids[i] >= id_begin && ids[i] < id_end;
+    const uint32_t m = __ballot_sync(0xffffffffu, removed);
+    if ((threadIdx.x & 31) == 0) {
+      if (i < n + 32) mask[i >> 5] = m;
+      cnt += __popc(m);
+    }
+  }
+  if ((threadIdx.x & 31) == 0) warp_cnt[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int w = 0; w < kMergeThreads / 32; ++w) t += warp_cnt[w];
+    tile_removed[blockIdx.x] = t;
+  }
+}
+// perm[rank of slot i among the survivors] = i (tile_base = exclusive scan of the removed counts per tile)
+__global__ void __launch_bounds__(kMergeThreads)
+remove_perm_kernel(uint32_t n, const uint32_t* __restrict__ mask, const uint32_t* __restrict__ tile_base, uint32_t* __restrict__ perm) {
+  constexpr int kWords = kMergeTile / 32;
+  __shared__ uint32_t wpre[kWords];
+  const uint32_t tile0 = blockIdx.x * (uint32_t)kMergeTile;
+  const uint32_t n_words = (n + 31) / 32, word0 = tile0 / 32;
+  if (threadIdx.x == 0) {  // 64 popcounts: a serial prefix is as fast as anything here
+    uint32_t run = 0;
+    for (int w = 0; w < kWords; ++w) {
+      wpre[w] = run;
+      if (word0 + w < n_words) run += __popc(mask[word0 + w]);
+    }
+  }
+  __syncthreads();
+  const uint32_t base = tile_base[blockIdx.x];
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int r = 0; r < kMergeTile / kMergeThreads; ++r) {
+    const uint32_t i = tile0 + r * kMergeThreads + threadIdx.x;
+    if (i >= n) break;
+    const uint32_t m = mask[i >> 5];
+    if ((m >> lane) & 1u) continue;
+    const uint32_t removed_before = base + wpre[(i - tile0) >> 5] + __popc(m & ((1u << lane) - 1u));
+    perm[i - removed_before] = i;
+  }
+}
+// ids stay the positions in upload order: those behind the removed range move down
+__global__ void __launch_bounds__(256) renumber_ids_kernel(uint32_t* __restrict__ ids, uint32_t n, uint32_t id_end, uint32_t removed) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && ids[i] >= id_end) ids[i] -= removed;
+}
+
 // out[0] = first sorted position whose key >= key_lo, out[1] = first whose key >= key_hi (slab handles:
 // the particles before out[0] / from out[1] on can reach the planes shared with a neighbour)
 __global__ void split_bounds_kernel(const uint32_t* __restrict__ keys, uint32_t count, uint32_t key_lo, uint32_t key_hi,

@@ -11,7 +11,8 @@
 //   * object lifetimes: the reference notices a changed active set only inside particlesToHost and
 //     then re-uploads stale data; here advance() activates an object at the first substep with
 //     t >= lifetime_begin by appending its particles on the device (mpm_append_particles_aos) and
-//     retires one at t >= lifetime_end by a download / re-upload of the remaining objects.
+//     retires one at t >= lifetime_end: its last state is read back into the host copy, then it is removed
+//     by a compaction on the device (mpm_remove_particles); the survivors are not re-uploaded.
 //   * syncDevice() downloads into the per-object vectors exactly like particlesToHost; the
 //     cheaper positions-only read-back for viewers is syncPositions().
 //   * errors are reported: every C-ABI failure throws std::runtime_error with mpm_last_error.
@@ -280,35 +281,35 @@ class Simulation {
   }
   void applyLifetimes() {
     const std::vector<size_t> now = activeNow();
-    bool only_additions = true;
+    // objects that ended: their last state goes to the host copies (as the reference's particlesToHost does when it
+    // notices the change), then they are removed on the device by a stable compaction — no re-upload, no re-bin;
+    // the upload order of the survivors closes up, exactly as uploaded_ does here
+    bool any_ended = false;
     for (size_t u : uploaded_) {
       bool still = false;
       for (size_t o : now) still = still || o == u;
-      only_additions = only_additions && still;
+      any_ended = any_ended || !still;
     }
-    if (only_additions) {  // objects entering: append on the device, nothing is read back
-      for (size_t o : now) {
-        bool have = false;
-        for (size_t u : uploaded_) have = have || u == o;
-        if (have) continue;
-        check(mpm_append_particles_aos(sim_, objects[o].particles.data(), objects[o].particles.size()));
-        uploaded_.push_back(o);
+    if (any_ended) syncDevice();
+    for (size_t k = 0; k < uploaded_.size();) {
+      bool still = false;
+      for (size_t o : now) still = still || o == uploaded_[k];
+      if (still) {
+        ++k;
+        continue;
       }
-    } else {  // an object ended: keep the survivors' current state, rebuild the device set
-      syncDevice();
-      std::vector<size_t> keep;
-      for (size_t u : uploaded_)
-        for (size_t o : now)
-          if (o == u) keep.push_back(u);
-      for (size_t o : now) {
-        bool have = false;
-        for (size_t u : keep) have = have || u == o;
-        if (!have) keep.push_back(o);
-      }
-      uploaded_ = keep;
-      host_.clear();
-      for (size_t o : uploaded_) host_.insert(host_.end(), objects[o].particles.begin(), objects[o].particles.end());
-      check(mpm_upload_particles_aos(sim_, host_.data(), host_.size()));
+      size_t first = 0;
+      for (size_t q = 0; q < k; ++q) first += objects[uploaded_[q]].particles.size();
+      check(mpm_remove_particles(sim_, first, objects[uploaded_[k]].particles.size()));
+      uploaded_.erase(uploaded_.begin() + (long)k);
+    }
+    // objects entering: appended on the device
+    for (size_t o : now) {
+      bool have = false;
+      for (size_t u : uploaded_) have = have || u == o;
+      if (have) continue;
+      check(mpm_append_particles_aos(sim_, objects[o].particles.data(), objects[o].particles.size()));
+      uploaded_.push_back(o);
     }
     active_particle_count = (int)uploaded_count();
   }

@@ -427,6 +427,48 @@ def test_overlapped_transfers_give_the_blocking_results():
     sim.close()
 
 
+def test_remove_particles_is_a_stable_compaction():
+    """mpm_remove_particles: the survivors keep their state and their cell order, the upload order closes up,
+    and the run continues as if the removed object had never been uploaded (it is far from the others here)."""
+    N = 32
+    rng = np.random.default_rng(9)
+    a = ol.new_particles(ol.sphere_positions(200000.0, 0.12, [0.3, 0.5, 0.3], rng))
+    b = ol.new_particles(ol.sphere_positions(200000.0, 0.10, [0.7, 0.5, 0.7], rng))   # removed later
+    c = ol.new_particles(ol.sphere_positions(200000.0, 0.08, [0.3, 0.3, 0.7], rng))
+    for q, vy in ((a, 1.0), (b, -2.0), (c, 0.5)):
+        q["v"][:, 1] = vy
+    mats = ol.make_material(1.0 / 200000.0)
+    everything = np.concatenate([a, b, c])
+    sim = _sim(N, mats, ol.SNOW, sort_every=4)
+    sim.upload(everything)
+    sim.advance(6)
+    before = sim.download()
+    k0, ids0 = sim.sort_state()
+    sim.remove(len(a), len(b))
+    assert sim.count == len(a) + len(c)
+    after = sim.download()
+    keep = np.r_[0:len(a), len(a) + len(b):len(everything)]
+    for f in ("x", "v", "F", "C", "Jp"):
+        assert np.array_equal(after[f], before[f][keep]), f
+    _, ids1 = sim.sort_state()
+    alive = (ids0 < len(a)) | (ids0 >= len(a) + len(b))
+    want_ids = ids0[alive]
+    want_ids = np.where(want_ids >= len(a) + len(b), want_ids - len(b), want_ids)
+    assert np.array_equal(ids1, want_ids)                        # same relative (cell) order, ids closed up
+    sim.advance(10)                                              # crosses re-bins (a full sort: the old keys are gone)
+    got = sim.download()
+    ref, _ = ol.advance(before[keep].copy(), mats, DT, N, ol.SNOW, 10)
+    assert np.abs(got["x"].astype(np.float64) - ref["x"]).max() * N < 1e-4
+    assert np.abs(got["v"].astype(np.float64) - ref["v"]).max() < 1e-3
+    sim.remove(0, sim.count)                                     # everything: an empty handle keeps working
+    assert sim.count == 0
+    sim.advance(2)
+    sim.upload(c)
+    sim.advance(2)
+    assert sim.count == len(c)
+    sim.close()
+
+
 def test_free_fall_velocity():
     """Oracle-free invariant: before contact v_y(t) = -9.81 t (SURVEY.md 8(c) pin 6)."""
     N = 32
