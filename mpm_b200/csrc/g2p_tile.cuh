@@ -43,9 +43,6 @@ constexpr int kG2pRows = NSTREAM - SX;  // stream rows x, F, Jp = 13, contiguous
 static_assert(SX == 12 && SF == 15 && SJ == 24, "G2P reads stream rows 12..24 as one span");
 
 #define MPM_STP(ptr, val) __stcs(ptr, val)  // particle streams are touched once per kernel: streaming stores
-#ifndef MPM_STREAM_HINTS
-#define MPM_STREAM_HINTS 1  // particle stream loads carry an evict-first hint as well
-#endif
 
 struct G2pTileLayout {
   // Jp is the last row: materials that never read it get a 12-row copy
@@ -279,11 +276,7 @@ g2p_tile_kernel(Soa p, const MatTable<Material> mats, const float4* __restrict__
   auto issue = [&](uint32_t t, int s) {
     tile_of[s] = t;
     mbar_arrive_expect_tx(full + s, (uint32_t)kStage);
-#if MPM_STREAM_HINTS
     bulk_g2s_hint(smem + s * kStage, p.tile(t) + SX * kTile, (uint32_t)kStage, full + s, l2_evict_first_policy());
-#else
-    bulk_g2s(smem + s * kStage, p.tile(t) + SX * kTile, (uint32_t)kStage, full + s);
-#endif
   };
   if (tid == 0) {
     for (int s = 0; s < kG2pStages; ++s) {

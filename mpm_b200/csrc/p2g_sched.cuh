@@ -30,20 +30,9 @@
 
 namespace mpm {
 
-#ifndef MPM_P2G_MINBLK
-#define MPM_P2G_MINBLK 4
-#endif
-#ifndef MPM_P2G_WARPSORT_MIN
-#define MPM_P2G_WARPSORT_MIN 4  // descents in a warp's key sequence from which the warp sorts
-#endif
-#ifndef MPM_STREAM_HINTS
-#define MPM_STREAM_HINTS 1  // particle streams are touched once per kernel: evict-first loads
-#endif
-#if MPM_STREAM_HINTS
-#define MPM_LDP(ptr) __ldcs(ptr)
-#else
-#define MPM_LDP(ptr) (*(ptr))
-#endif
+constexpr int kP2gMinBlocks = 4;    // CTAs per SM the kernel is compiled for (64 registers; 48 spill, 80 lose a CTA: profiles/r01_ab2, r02_ab5)
+constexpr int kP2gWarpSortMin = 4;  // descents in a warp's key sequence from which the warp sorts
+#define MPM_LDP(ptr) __ldcs(ptr)    // particle streams are touched once per kernel: evict-first loads
 constexpr int kP2gBlock = kTile;
 constexpr int kRunPosBits = 8;  // run list entry = first particle | (length - 1) << kRunPosBits
 constexpr uint32_t kInvalidKey = 0xffffffffu;
@@ -140,7 +129,7 @@ __device__ __forceinline__ void p2g_warp_order(uint32_t key, int tid, uint16_t* 
     // (one or two stragglers do not pay for a sort: the warp's sort delays its whole CTA at the next barrier,
     // profiles/r02_ab4_p2g_warpsort.txt)
     const uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
-    if (__popc(__ballot_sync(0xffffffffu, lane > 0 && prev > key)) >= MPM_P2G_WARPSORT_MIN) {
+    if (__popc(__ballot_sync(0xffffffffu, lane > 0 && prev > key)) >= kP2gWarpSortMin) {
       const uint2 r = p2g_warp_sort(key, tid, scratch);
       pos = (int)r.x;
       skey = r.y;
@@ -277,7 +266,7 @@ struct MaterialTraits<MMFixedCorotated<P, O>> {
 // SORT: the launch was told that the order has gone stale (the host decides from the cell crossings G2P
 // counts since the last re-bin): warps re-order their payload records first (p2g_warp_order)
 template <class Material, bool ONE_MAT, bool HANDOVER, bool SORT>
-__global__ void __launch_bounds__(kP2gBlock, MPM_P2G_MINBLK)
+__global__ void __launch_bounds__(kP2gBlock, kP2gMinBlocks)
 p2g_sched_kernel(Soa p, size_t count, const MatTable<Material> mats, float4* __restrict__ grid, KParams k,
                  uint32_t* __restrict__ sort_keys, uint32_t* __restrict__ sort_vals, uint32_t first, DeviceDiag* __restrict__ diag) {
   __shared__ P2gSmem sm;

@@ -148,11 +148,9 @@ __global__ void __launch_bounds__(kScanThreads) scan_downsweep_kernel(uint32_t* 
 
 // (c) stable scatter.  Warp w owns the contiguous chunk [tile0 + w*256, +256) of its tile and
 // walks it 32 keys at a time, so (warp, iteration, lane) order is the input order.
-#ifndef MPM_SCATTER_MINBLK
-#define MPM_SCATTER_MINBLK 5
-#endif
+constexpr int kScatterMinBlocks = 5;
 template <int BITS>
-__global__ void __launch_bounds__(kSortThreads, BITS == 8 ? MPM_SCATTER_MINBLK : 4)
+__global__ void __launch_bounds__(kSortThreads, BITS == 8 ? kScatterMinBlocks : 4)
 radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ keys_out,
                      uint32_t* __restrict__ vals_out, size_t count, int shift, const uint32_t* __restrict__ table, int n_tiles) {
   constexpr int kRadix = 1 << BITS;

@@ -19,11 +19,8 @@ __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-#ifndef MPM_MBAR_HINT
-#define MPM_MBAR_HINT 1  // 1: try_wait carries a suspend-time hint, so a waiting warp sleeps in hardware instead of re-issuing the probe
-#endif
+// try_wait carries a suspend-time hint, so a waiting warp sleeps in hardware instead of re-issuing the probe
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-#if MPM_MBAR_HINT
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
@@ -35,19 +32,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "}\n" ::"r"(smem_u32(bar)),
       "r"(parity), "r"(0x989680u)
       : "memory");
-#else
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-#endif
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t done;
