@@ -369,17 +369,19 @@ def timed(ctx, sim, steps, warmup):
     return ms, sim.launches - launches0, (t0, time.monotonic())
 
 
-def short_leg(ctx, model, scaling, svd, steps, shear=0.0, f_noise=0.0, particles=P_PER_GPU, sort_every=8):
+def short_leg(ctx, model, scaling, svd, steps, shear=0.0, f_noise=0.0, particles=P_PER_GPU, sort_every=8, rebin_permille=0):
     """One more workload, measured like the main one but shorter; returns a small dict."""
     ghost = 0
     if shear and ctx.world > 1:
         # slab handles: the fastest particles (0.4 shear m/s at the block faces) must stay within the ghost
         # planes between two re-bins, or the re-bin fails (MpmDiagnostics.escaped): 2 ghost planes, cadence 4
         ghost, sort_every = 2, 4
-    sim, N, slabs, P_total, _ = make_sim(ctx, model, scaling, particles, svd, sort_every, ghost=ghost)
+    sim, N, slabs, P_total, _ = make_sim(ctx, model, scaling, particles, svd, sort_every, ghost=ghost, rebin_permille=rebin_permille)
     sim.generate_dense_block(P_total, seed=1234, shear=shear, f_noise=f_noise)
     sim.sync()
+    rebins0 = sim.rebins
     ms, _, _ = timed(ctx, sim, steps, 8)
+    rebins = sim.rebins - rebins0
     P_all = ctx.reduce([float(sim.count)])[0]
     diag = sim.diagnostics()
     sim.close()
@@ -387,7 +389,8 @@ def short_leg(ctx, model, scaling, svd, steps, shear=0.0, f_noise=0.0, particles
         ctx.fail(f"{model}/{scaling}: {P_all} particles on the ranks, {P_total} generated")
     return {"N": N, "particles": int(P_all), "model": model, "svd_mode": svd, "scaling": scaling if ctx.world > 1 else "n/a",
             "ms_per_step": ms / steps, "value": P_all / (ms / steps * 1e-3), "unit": "particle-steps/s", "steps": steps,
-            "shear": shear, "f_noise": f_noise, "sort_every": sort_every, "ghost": ghost, "nonfinite": diag["nonfinite"]}
+            "shear": shear, "f_noise": f_noise, "sort_every": sort_every, "rebin_permille": rebin_permille, "rebins": int(rebins),
+            "ghost": ghost, "nonfinite": diag["nonfinite"]}
 
 
 def parity_nranks(ctx):
@@ -668,6 +671,11 @@ def main():
         }
         if world == 1:
             stressed["snow_exact_svd"] = short_leg(ctx, "snow", args.scaling, "exact", 8)
+            # re-bin on measured disorder instead of a fixed cadence (MpmParams.rebin_permille: when the cell crossings
+            # G2P counts since the last re-bin pass 5 % of the particles); `rebins` = re-bins in warm-up + timed substeps
+            configs["adaptive_rebin_at_rest"] = short_leg(ctx, "fixed_corotated", args.scaling, "fast", k, sort_every=0, rebin_permille=50)
+            stressed["adaptive_rebin_sheared"] = short_leg(ctx, "fixed_corotated", args.scaling, "fast", k, shear=20.0, f_noise=0.05,
+                                                           sort_every=0, rebin_permille=50)
     small = small_scenes() if (full and world == 1) else None
 
     if rank == 0:

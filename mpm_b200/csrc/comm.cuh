@@ -241,7 +241,7 @@ struct Comm {
     if (r != ncclSuccess) return fail("ncclGroupEnd(counts)", r);
     r = ncclAllReduce(d_escaped, d_counts + 4, 1, ncclUint32, ncclSum, comm, stream);
     if (r != ncclSuccess) return fail("ncclAllReduce(escaped)", r);
-    e = cudaMemcpyAsync(h_counts, d_counts, sizeof(unsigned int) * 8, cudaMemcpyDeviceToHost, stream);
+    e = readback_words(h_counts, d_counts, 8, stream);
     if (e != cudaSuccess) return failc("memcpy(counts)", e);
     e = cudaStreamSynchronize(stream);
     if (e != cudaSuccess) return failc("sync(counts)", e);

@@ -61,6 +61,19 @@ struct KParams {
   __host__ __device__ SimulationParameters par() const { return SimulationParameters(dt, (u32)N); }
 };
 
+// Small read-backs of the substep path (counters the host decides by) are STORED into pinned host memory by
+// this kernel instead of copied by cudaMemcpyAsync: a device -> host copy of a few bytes would queue in the
+// copy engine behind a 7 GB read-back of the particle state that is in flight on another stream
+// (mpm_download_particles_aos_async) and stall the substeps for its whole duration.
+static __global__ void __launch_bounds__(32) store_words_to_host_kernel(const uint32_t* __restrict__ src, volatile uint32_t* dst, int n) {
+  if ((int)threadIdx.x < n) dst[threadIdx.x] = src[threadIdx.x];
+  __threadfence_system();
+}
+inline cudaError_t readback_words(void* host_pinned, const void* dev, int n_words, cudaStream_t stream) {
+  store_words_to_host_kernel<<<1, 32, 0, stream>>>(static_cast<const uint32_t*>(dev), static_cast<volatile uint32_t*>(host_pinned), n_words);
+  return cudaGetLastError();
+}
+
 constexpr uint32_t kDeadId = 0xffffffffu;  // tombstone of a particle that migrated to another rank
 
 // counters the kernels keep for the host (mpm_get_diagnostics); device memory, one per handle

@@ -381,7 +381,7 @@ uint32_t* merge_pairs(MpmSim* sim, size_t n, size_t n_old, int* rc) {
   exclusive_scan_total_kernel<<<1, 1024, 0, sim->stream>>>(sim->tile_moved, n_tiles, sim->d_n_moved);
   sim->launches += 2;
   uint32_t* h_n = reinterpret_cast<uint32_t*>(sim->h_moved);  // pinned scratch
-  if (cudaMemcpyAsync(h_n, sim->d_n_moved, sizeof(uint32_t), cudaMemcpyDeviceToHost, sim->stream) != cudaSuccess ||
+  if (readback_words(h_n, sim->d_n_moved, 1, sim->stream) != cudaSuccess ||
       cudaStreamSynchronize(sim->stream) != cudaSuccess) {
     *rc = 1;
     return nullptr;
@@ -472,7 +472,7 @@ int do_sort(MpmSim* sim, bool partial = false, bool keys_ready = false) {
     const uint32_t key_hi = sim->comm.has_hi ? (uint32_t)std::max(0, sim->k.x_own_end - 2 - 2 * g - sim->k.x0) * NN : 0xffffffffu;
     split_bounds_kernel<<<1, 32, 0, sim->stream>>>(sim->okeys[sim->ocur], (uint32_t)sim->count, key_lo, key_hi, sim->d_split);
     sim->launches++;
-    CK(cudaMemcpyAsync(sim->h_split, sim->d_split, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, sim->stream));
+    CK(readback_words(sim->h_split, sim->d_split, 2, sim->stream));
     CK(cudaEventRecord(sim->split_ev, sim->stream));
     sim->split_pending = true;
     sim->split_valid = false;
@@ -1084,7 +1084,7 @@ static int advance_impl(MpmSim* sim, int n_substeps) {
     // hand-over: every G2P but the last of this call leaves the next P2G's affine matrix in the C rows
     if (int rc = do_g2p(sim, sim->handover && s + 1 < n_substeps)) return rc;
     if (track && !sim->moved_pending) {
-      CK(cudaMemcpyAsync(sim->h_moved, sim->d_moved, sizeof(unsigned long long), cudaMemcpyDeviceToHost, sim->stream));
+      CK(readback_words(sim->h_moved, sim->d_moved, 2, sim->stream));
       CK(cudaEventRecord(sim->moved_ev, sim->stream));
       sim->moved_pending = true;
       sim->moved_issued_at = sim->substeps;
