@@ -153,10 +153,11 @@ int mpm_download_particles_aos_async(MpmSim* sim, MpmParticle* particles, size_t
 int mpm_download_wait(MpmSim* sim);
 /* positions only (12 B/particle), upload order — what the reference's viewer cadence needs */
 int mpm_download_positions(MpmSim* sim, float* xyz, size_t capacity, size_t* count);
-/* the same without blocking: the copy is queued behind the substeps issued so far and overlaps the
- * ones issued afterwards only if xyz is pinned host memory; read it after mpm_sync().  This is the
- * reference's viewer cadence (src/main.cu:99-102) without stalling the substep pipeline.  The staging
- * buffer is shared with the other transfers: one transfer in flight at a time. */
+/* the same without blocking: the copy is queued behind the substeps issued so far and runs on a copy stream
+ * of its own, so the substeps issued afterwards overlap it (xyz must be pinned host memory for that); read
+ * the buffer after mpm_sync() or mpm_download_wait().  This is the reference's viewer cadence
+ * (src/main.cu:99-102) without stalling the substep pipeline.  The staging buffer is shared with the other
+ * read-backs: a second one queues behind the first. */
 int mpm_download_positions_async(MpmSim* sim, float* xyz, size_t capacity, size_t* count);
 /* synthetic dense block generated on the device: ids
  * [first_id, first_id+count), x = lo + (hi-lo)*u(hash(seed,id,axis)), v=0, F=I, C=0, Jp=1;

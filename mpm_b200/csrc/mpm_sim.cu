@@ -982,18 +982,23 @@ int mpm_download_positions_async(MpmSim* sim, float* xyz, size_t capacity, size_
   if (count) *count = sim->count;
   if (capacity < sim->count) return fail(sim, "mpm_download_positions: capacity too small");
   if (sim->count == 0) return 0;
+  if (int rc = io_objects(sim)) return rc;
   if (int rc = ensure_stage(sim, (sim->count * 12 + sizeof(MpmParticle) - 1) / sizeof(MpmParticle))) return rc;
   float* stage = reinterpret_cast<float*>(sim->aos_stage);
   positions_kernel<<<blocks_for(sim->count, 256), 256, 0, sim->stream>>>(sim->soa[sim->cur], sim->count, stage, sim->first_id, sim->whole_domain);
   sim->launches++;
   CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(xyz, stage, sizeof(float) * 3 * sim->count, cudaMemcpyDeviceToHost, sim->stream));
+  // the copy runs on the read-back stream: substeps issued after this call do not wait for it
+  CK(cudaEventRecord(sim->ev_staged, sim->stream));
+  CK(cudaStreamWaitEvent(sim->io_out, sim->ev_staged, 0));
+  CK(cudaMemcpyAsync(xyz, stage, sizeof(float) * 3 * sim->count, cudaMemcpyDeviceToHost, sim->io_out));
+  CK(cudaEventRecord(sim->ev_downloaded, sim->io_out));
+  sim->download_pending = true;
   return 0;
 }
 int mpm_download_positions(MpmSim* sim, float* xyz, size_t capacity, size_t* count) {
   if (int rc = mpm_download_positions_async(sim, xyz, capacity, count)) return rc;
-  CK(cudaStreamSynchronize(sim->stream));
-  return 0;
+  return mpm_download_wait(sim);
 }
 
 int mpm_generate_dense_block_stressed(MpmSim* sim, uint64_t first_id, uint64_t count, uint32_t seed, float lo, float hi, uint8_t material,
@@ -1173,6 +1178,10 @@ int mpm_sync(MpmSim* sim) {
   if (!sim) return 1;
   CK(cudaSetDevice(sim->device));
   CK(cudaStreamSynchronize(sim->stream));
+  if (sim->download_pending) {  // read-backs queued by the *_async calls
+    CK(cudaEventSynchronize(sim->ev_downloaded));
+    sim->download_pending = false;
+  }
   return 0;
 }
 
