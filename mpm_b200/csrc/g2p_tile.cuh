@@ -34,10 +34,7 @@
 
 namespace mpm {
 
-#ifndef MPM_G2P_STAGES
-#define MPM_G2P_STAGES 3
-#endif
-constexpr int kG2pStages = MPM_G2P_STAGES;
+constexpr int kG2pStages = 3;  // (2 and 4 measured in round 1: no better)
 constexpr int kG2pThreads = kTile;
 constexpr int kG2pRows = NSTREAM - SX;  // stream rows x, F, Jp = 13, contiguous in a tile
 static_assert(SX == 12 && SF == 15 && SJ == 24, "G2P reads stream rows 12..24 as one span");
