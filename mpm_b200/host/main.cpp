@@ -5,7 +5,9 @@
 // loop, which the reference runs until it is killed.
 #include <sys/stat.h>
 
+#include <future>
 #include <iomanip>
+#include <memory>
 #include <sstream>
 
 #include "output.hpp"
@@ -39,6 +41,7 @@ int main(int argc, char* argv[]) {
     const u32 frame_rate = flags.frame_rate ? flags.frame_rate : FrameRateDefault;
     const u32 save_every = std::max<u32>(1, u32(1. / float(frame_rate) / flags.dt));
     u32 frame_id = 0;
+    std::future<void> output;  // the frame being written
     const unsigned long long n_steps = flags.steps >= 0 ? (unsigned long long)flags.steps : std::numeric_limits<u32>::max();
     for (unsigned long long i = 0; i < n_steps; i++) {
       if (i % 10 == 0) std::cout << "Step " << i << "\r" << std::flush;
@@ -46,16 +49,25 @@ int main(int argc, char* argv[]) {
       const bool frame = save && (i % save_every) == 0;
       if (i % flags.sync_every == 0 || frame) simulation.syncDevice();
       if (frame) {
+        // the frame's files are written from a snapshot by a second host thread, so that the substeps of the next
+        // frame (queued asynchronously by advance()) and the meshing / file I/O of this one overlap; one frame in flight
         std::stringstream ss;
         ss << flags.save_dir << "/meshes/mesh_" << std::setfill('0') << std::setw(5) << frame_id << ".obj";
-        mesher.computeMesh(ss.str(), simulation.getActiveParticleList());
+        const std::string mesh_path = ss.str();
         ss.str("");
         ss.clear();
         ss << flags.save_dir << "/particles/particles_" << frame_id << "." << flags.particle_format;
-        writer.writeParticles(ss.str(), simulation.getActiveParticleList());
+        const std::string particle_path = ss.str();
+        if (output.valid()) output.get();
+        auto snapshot = std::make_shared<std::vector<Particle>>(simulation.getActiveParticleList());
+        output = std::async(std::launch::async, [&mesher, &writer, snapshot, mesh_path, particle_path] {
+          mesher.computeMesh(mesh_path, *snapshot);
+          writer.writeParticles(particle_path, *snapshot);
+        });
         frame_id++;
       }
     }
+    if (output.valid()) output.get();
     simulation.syncDevice();
     std::cout << "\ndone: " << n_steps << " substeps, t = " << simulation.t << ", " << simulation.getActiveParticleList().size() << " active particles"
               << std::endl;
