@@ -14,6 +14,7 @@
 // torus (any other name -> UV sphere).  All stand-ins are single closed non-self-intersecting
 // surfaces, so the winding number is 0 or 1.
 #pragma once
+#include <charconv>
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -94,13 +95,47 @@ inline bool read_obj(const std::string& path, TriMesh& m, std::string* err = nul
 }
 
 // OBJ text as igl::writeOBJ emits it (include/igl/writeOBJ.cpp:42-47, 78-94): %0.17g vertices, 1-based faces
+// "v %0.17g %0.17g %0.17g" / "f %d %d %d" (1-based) lines; std::to_chars(general, 17) produces the characters of
+// %.17g, chunks are formatted in parallel and written in order
 inline bool write_obj(const std::string& path, const std::vector<double>& V, const std::vector<int>& F) {
   FILE* f = std::fopen(path.c_str(), "w");
   if (!f) return false;
-  for (size_t i = 0; i + 2 < V.size(); i += 3) std::fprintf(f, "v %0.17g %0.17g %0.17g\n", V[i], V[i + 1], V[i + 2]);
-  for (size_t i = 0; i + 2 < F.size(); i += 3) std::fprintf(f, "f %d %d %d\n", F[i] + 1, F[i + 1] + 1, F[i + 2] + 1);
-  std::fclose(f);
-  return true;
+  const size_t nv = V.size() / 3, nf = F.size() / 3, chunk = 1u << 13;
+  const size_t cv = (nv + chunk - 1) / chunk, cf = (nf + chunk - 1) / chunk;
+  std::vector<std::string> parts(cv + cf);
+#pragma omp parallel for schedule(dynamic)
+  for (long long c = 0; c < (long long)(cv + cf); ++c) {
+    std::string& out = parts[(size_t)c];
+    char buf[40];
+    if ((size_t)c < cv) {
+      const size_t b = (size_t)c * chunk, e = std::min(nv, b + chunk);
+      out.reserve((e - b) * 72);
+      for (size_t i = b; i < e; ++i) {
+        out += 'v';
+        for (int d = 0; d < 3; ++d) {
+          out += ' ';
+          const auto r = std::to_chars(buf, buf + sizeof(buf), V[3 * i + d], std::chars_format::general, 17);
+          out.append(buf, r.ptr);
+        }
+        out += '\n';
+      }
+    } else {
+      const size_t b = ((size_t)c - cv) * chunk, e = std::min(nf, b + chunk);
+      out.reserve((e - b) * 28);
+      for (size_t i = b; i < e; ++i) {
+        out += 'f';
+        for (int d = 0; d < 3; ++d) {
+          out += ' ';
+          const auto r = std::to_chars(buf, buf + sizeof(buf), F[3 * i + d] + 1);
+          out.append(buf, r.ptr);
+        }
+        out += '\n';
+      }
+    }
+  }
+  bool ok = true;
+  for (const std::string& part : parts) ok = ok && std::fwrite(part.data(), 1, part.size(), f) == part.size();
+  return std::fclose(f) == 0 && ok;
 }
 
 // ---- procedural stand-ins (outward-facing triangles) ----

@@ -17,6 +17,9 @@
 //     tests compare enclosed volume and closedness.
 //   * --laplacian_smooth and --mesh-face-count (mesh_builder.h:196-211) are mesh_ops.hpp.
 #pragma once
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -128,24 +131,36 @@ class ParticleWriter {
 
 // fillVoxelGrid_distance (mesh_builder.h:89-138): float arithmetic, C truncation of the ranges
 inline void fill_voxel_grid_distance(const std::vector<Particle>& particles, real dx, real distance_cutoff, int G, std::vector<float>& grid) {
-  grid.assign((size_t)G * G * G, distance_cutoff);
+  grid.resize((size_t)G * G * G);
   const real r_gridpoints = distance_cutoff / dx;
-  for (const Particle& particle : particles) {
-    int b[3], e[3];
-    for (int d = 0; d < 3; ++d) {
-      const real xg = particle.x[d] / dx;
-      b[d] = std::max(0, (int)(xg - r_gridpoints));
-      e[d] = std::min(G, (int)(xg + (r_gridpoints + 1.0f)));
-    }
-    for (int i = b[0]; i < e[0]; ++i) {
-      const real dxn = particle.x[0] - i * dx;
-      for (int j = b[1]; j < e[1]; ++j) {
-        const real dyn = particle.x[1] - j * dx;
-        for (int k = b[2]; k < e[2]; ++k) {
-          const real dzn = particle.x[2] - k * dx;
-          const real dist = std::sqrt(dxn * dxn + dyn * dyn + dzn * dzn);
-          float& g = grid[((size_t)i * G + j) * G + k];
-          g = std::min(dist, g);
+  // every thread owns a range of i-planes and clips each particle's box to it: min() is order-independent, so
+  // the result is the sequential one without atomics
+#pragma omp parallel
+  {
+#ifdef _OPENMP
+    const int nt = omp_get_num_threads(), me = omp_get_thread_num();
+#else
+    const int nt = 1, me = 0;
+#endif
+    const int i0 = (int)((long long)G * me / nt), i1 = (int)((long long)G * (me + 1) / nt);
+    std::fill(grid.begin() + (size_t)i0 * G * G, grid.begin() + (size_t)i1 * G * G, distance_cutoff);
+    for (const Particle& particle : particles) {
+      int b[3], e[3];
+      for (int d = 0; d < 3; ++d) {
+        const real xg = particle.x[d] / dx;
+        b[d] = std::max(0, (int)(xg - r_gridpoints));
+        e[d] = std::min(G, (int)(xg + (r_gridpoints + 1.0f)));
+      }
+      for (int i = std::max(b[0], i0); i < std::min(e[0], i1); ++i) {
+        const real dxn = particle.x[0] - i * dx;
+        for (int j = b[1]; j < e[1]; ++j) {
+          const real dyn = particle.x[1] - j * dx;
+          for (int k = b[2]; k < e[2]; ++k) {
+            const real dzn = particle.x[2] - k * dx;
+            const real dist = std::sqrt(dxn * dxn + dyn * dyn + dzn * dzn);
+            float& g = grid[((size_t)i * G + j) * G + k];
+            g = std::min(dist, g);
+          }
         }
       }
     }
@@ -192,16 +207,21 @@ inline void marching_tetrahedra(const std::vector<double>& S, int G, std::vector
   };
   // cube corners: bit 0 = +i, bit 1 = +j, bit 2 = +k; six tetrahedra sharing the diagonal 0-7
   static const int tets[6][4] = {{0, 1, 3, 7}, {0, 3, 2, 7}, {0, 2, 6, 7}, {0, 6, 4, 7}, {0, 4, 5, 7}, {0, 5, 1, 7}};
-  for (int i = 0; i + 1 < G; ++i)
+  // the cells the surface passes through, found plane by plane in parallel and visited in lattice order
+  std::vector<std::vector<int>> crossed(G > 1 ? G - 1 : 0);
+#pragma omp parallel for schedule(dynamic, 4)
+  for (int i = 0; i < G - 1; ++i)
     for (int j = 0; j + 1 < G; ++j)
       for (int k = 0; k + 1 < G; ++k) {
-        size_t c[8];
         int n_in = 0;
-        for (int q = 0; q < 8; ++q) {
-          c[q] = lattice(i + (q & 1), j + ((q >> 1) & 1), k + ((q >> 2) & 1));
-          n_in += S[c[q]] > 0.0;
-        }
-        if (n_in == 0 || n_in == 8) continue;
+        for (int q = 0; q < 8; ++q) n_in += S[lattice(i + (q & 1), j + ((q >> 1) & 1), k + ((q >> 2) & 1))] > 0.0;
+        if (n_in != 0 && n_in != 8) crossed[i].push_back(j * G + k);
+      }
+  for (int i = 0; i + 1 < G; ++i)
+    for (int jk : crossed[i]) {
+        const int j = jk / G, k = jk % G;
+        size_t c[8];
+        for (int q = 0; q < 8; ++q) c[q] = lattice(i + (q & 1), j + ((q >> 1) & 1), k + ((q >> 2) & 1));
         for (auto& tet : tets) {
           size_t in[4], out[4];
           int ni = 0, no = 0;
@@ -233,7 +253,8 @@ class MeshBuilder {
     std::vector<float> sdf;
     fill_voxel_grid_distance(particles, (real)voxel_dx, (real)((flags_.mesh_particle_radius + 1) * voxel_dx), G, sdf);
     std::vector<double> S(sdf.size());
-    for (size_t q = 0; q < sdf.size(); ++q) S[q] = flags_.mesh_particle_radius * voxel_dx - double(sdf[q]);
+#pragma omp parallel for schedule(static)
+    for (long long q = 0; q < (long long)sdf.size(); ++q) S[q] = flags_.mesh_particle_radius * voxel_dx - double(sdf[q]);
     std::vector<double> V;
     std::vector<int> F;
     marching_tetrahedra(S, G, V, F);
