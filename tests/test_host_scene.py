@@ -211,6 +211,8 @@ def test_mesh_builder_and_particle_writer(tmp_path):
     V = np.array([l.split()[1:] for l in open(tmp_path / "m.obj") if l.startswith("v ")], np.float64)
     F = np.array([l.split()[1:] for l in open(tmp_path / "m.obj") if l.startswith("f ")], np.int64) - 1
     assert len(V) == nv and len(F) == nf
+    toks = [t for l in open(tmp_path / "m.obj") if l.startswith("v ") for t in l.split()[1:]]
+    assert all(t == "%0.17g" % float(t) for t in toks)           # the writer's own formatter prints what %0.17g prints
     counts, volume = _mesh_checks(V, F)
     assert (counts == 2).all() and volume > 0
     x = s.active_particles()["x"]
