@@ -379,7 +379,7 @@ uint32_t* merge_pairs(MpmSim* sim, size_t n, size_t n_old, int* rc) {
   const unsigned n_tiles = blocks_for(n, kMergeTile);
   rebin_flags_kernel<<<n_tiles, kMergeThreads, 0, sim->stream>>>(newk, oldk, (uint32_t)n, (uint32_t)n_old, sim->mmask, sim->tile_moved);
   exclusive_scan_total_kernel<<<1, 1024, 0, sim->stream>>>(sim->tile_moved, n_tiles, sim->d_n_moved);
-  sim->launches += 2;
+  sim->launches += 3;  // (with the read-back kernel below)
   uint32_t* h_n = reinterpret_cast<uint32_t*>(sim->h_moved);  // pinned scratch
   if (readback_words(h_n, sim->d_n_moved, 1, sim->stream) != cudaSuccess ||
       cudaStreamSynchronize(sim->stream) != cudaSuccess) {
@@ -473,6 +473,7 @@ int do_sort(MpmSim* sim, bool partial = false, bool keys_ready = false) {
     split_bounds_kernel<<<1, 32, 0, sim->stream>>>(sim->okeys[sim->ocur], (uint32_t)sim->count, key_lo, key_hi, sim->d_split);
     sim->launches++;
     CK(readback_words(sim->h_split, sim->d_split, 2, sim->stream));
+    sim->launches++;
     CK(cudaEventRecord(sim->split_ev, sim->stream));
     sim->split_pending = true;
     sim->split_valid = false;
@@ -1090,6 +1091,7 @@ static int advance_impl(MpmSim* sim, int n_substeps) {
     if (int rc = do_g2p(sim, sim->handover && s + 1 < n_substeps)) return rc;
     if (track && !sim->moved_pending) {
       CK(readback_words(sim->h_moved, sim->d_moved, 2, sim->stream));
+      sim->launches++;
       CK(cudaEventRecord(sim->moved_ev, sim->stream));
       sim->moved_pending = true;
       sim->moved_issued_at = sim->substeps;
