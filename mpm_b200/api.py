@@ -41,11 +41,29 @@ _vp = ctypes.c_void_p
 _fp = ctypes.POINTER(ctypes.c_float)
 
 
+def _preload_nccl():
+    """The library depends on libnccl.so.2 by soname.  A PyTorch imported later in the same process needs the NCCL
+    it ships with (newer than the system one), and the first libnccl.so.2 loaded wins — so load that one first
+    when it is installed; otherwise the system library is found the usual way."""
+    import importlib.util
+
+    try:
+        spec = importlib.util.find_spec("nvidia")
+        for base in (spec.submodule_search_locations if spec else []):
+            cand = os.path.join(base, "nccl", "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                ctypes.CDLL(cand, mode=ctypes.RTLD_GLOBAL)
+                return
+    except Exception:
+        pass
+
+
 def lib():
     """Loads (building if needed) libmpm_b200.so.  Raises if it cannot be had — no fallback."""
     global _lib
     if _lib is None:
         path = os.environ.get("MPM_B200_LIB") or _build.build()  # MPM_B200_LIB: experiment builds (tools/ab.py)
+        _preload_nccl()
         L = ctypes.CDLL(path)
         L.mpm_last_error.restype = ctypes.c_char_p
         L.mpm_last_error.argtypes = [_vp]
